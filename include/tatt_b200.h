@@ -1,0 +1,141 @@
+/* tatt_b200 -- C-ABI of the B200-native (sm_100a) TATT/TSRN hot path.
+ *
+ * Boundary contract: plain device pointers + sizes, the caller's CUDA stream as the
+ * last argument (a cudaStream_t passed as void*), no torch types.  Every tensor is fp32, contiguous,
+ * device-resident, caller-allocated and caller-owned; nothing is retained after the call returns
+ * (all work is enqueued on `stream`).  Entry points return 0 on success and a non-zero code on
+ * failure; `tatt_last_error()` then returns a thread-local message.  Nothing throws, nothing exits.
+ * The library keeps no global mutable state and is re-entrant (DataParallel-style callers,
+ * interfaces/base.py:390 in the reference, call replicas from several threads).
+ *
+ * The reference (mjq11302010044/TATT) is pure Python; it has no FFI.  Each group below names the
+ * reference nn.Module / functional call (file:line under the reference tree) whose arithmetic it
+ * replaces.  Feature maps are channels-last ("NHWC": [N][H][W][C]); token tensors are [N][L][64].
+ */
+#ifndef TATT_B200_H_
+#define TATT_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* tatt_last_error(void);
+int tatt_version(void);
+/* 1 when the library was compiled for sm_100a (always, in this tree) */
+int tatt_arch(void);
+
+/* ---- GEMM / linear layers: nn.Linear, 1x1 nn.Conv2d, GRU input/recurrent projections -------------
+ * model/tsrn.py:170,1070 ; model/transformer_v2.py:453-458,785-790,177 ; model/stn_head.py:49-53
+ * amode: 0 A[M][K] row-major, 1 A given as [K][M].  bmode: 0 B[K][N], 1 B given as [N][K].
+ * flags: 1 accumulate into C, 2 ReLU epilogue, 4 split-K with atomics (C must be zero, or add 64 to
+ * have a dense C zeroed here).  batch > 1 strides A/B/C/bias by sA/sB/sC/sBias elements. */
+int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* B, long long ldb, float* C,
+              long long ldc, const float* bias, int M, int N, int K, int batch, long long sA, long long sB,
+              long long sC, long long sBias, int flags, void* stream);
+/* out[c] (+)= sum_r X[r*ldx + c] */
+int tatt_colsum(const float* X, long long ldx, float* out, long long P, int C, int zero_first, void* stream);
+
+/* ---- convolution (stride 1), implicit GEMM over NHWC: nn.Conv2d ------------------------------------
+ * model/tsrn.py:597 (9x9 stem), 876,884 (SRB 3x3), 611 (block7), 1043 (upsample 64->256), 623 (9x9 out);
+ * model/stn_head.py:15.  Weights are first packed to Wt[(ky,kx,ci)][co] (flip=0) or, for the
+ * data-gradient, to the flipped/transposed Wt[(ky,kx,co)][ci] (flip=1). */
+int tatt_conv_weight_pack(const float* W, float* Wt, int Cout, int Cin, int KH, int KW, int CinP, int CoutP,
+                          int flip, void* stream);
+int tatt_conv_weight_unpack_grad(const float* dWt, float* dW, int Cout, int Cin, int KH, int KW, int CinP,
+                                 int CoutP, void* stream);
+int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W, int Cin,
+                      int Cout, int KH, int KW, int padH, int padW, int flags, void* stream);
+int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cin, int Cout,
+                      int KH, int KW, int padH, int padW, void* stream);
+
+/* ---- BatchNorm (batch statistics over all rows of X[P][C]) with fused activation ----------------------
+ * nn.BatchNorm2d/1d: model/tsrn.py:878,886,612 ; model/stn_head.py:19,51.  act: 0 none, 1 ReLU, 2 mish
+ * (model/tsrn.py:1061-1064).  ws: scratch of >= 2*C doubles. */
+int tatt_bn_stats(const float* X, long long P, int C, float eps, float momentum, float* mean, float* invstd,
+                  float* running_mean, float* running_var, void* ws, void* stream);
+int tatt_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
+                       float* invstd, void* stream);
+int tatt_bn_apply_fwd(const float* X, float* Y, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, int act, long long P, int C, void* stream);
+int tatt_bn_bwd(const float* X, const float* dY, const float* mean, const float* invstd, const float* gamma,
+                const float* beta, int act, int training, long long P, int C, float* dX, float* dgamma,
+                float* dbeta, void* ws, void* stream);
+
+/* ---- LayerNorm(64) with fused residual add: model/transformer_v2.py:460-461,792-794,166 -------------- */
+int tatt_layernorm64_fwd(const float* X, const float* R, const float* gamma, const float* beta, float* Y, float* S,
+                         float* mean, float* rstd, long long P, float eps, void* stream);
+int tatt_layernorm64_bwd(const float* dY, const float* S, const float* mean, const float* rstd, const float* gamma,
+                         float* dS, float* dgamma, float* dbeta, long long P, void* stream);
+
+/* ---- BiGRU(hidden 32) scans on the NHWC map: GruBlock, model/tsrn.py:1067-1084 ------------------------
+ * GI [rows][192], OUT [rows][64], GATES [rows][320] (saved for bwd), dGI/dGH [rows][192];
+ * row(seq,t) = (seq / s_inner)*outer_stride + (seq % s_inner)*inner_stride + t*t_stride. */
+int tatt_gru32_scan_fwd(const float* GI, const float* Whh, const float* bhh, float* OUT, float* GATES, int nseq,
+                        int T, int s_inner, long long outer_stride, long long inner_stride, long long t_stride,
+                        void* stream);
+int tatt_gru32_scan_bwd(const float* dOUT, const float* GATES, const float* Whh, float* dGI, float* dGH, int nseq,
+                        int T, int s_inner, long long outer_stride, long long inner_stride, long long t_stride,
+                        void* stream);
+
+/* ---- recurrent positional encoding (batch-axis BiGRU, quirk Q1): model/transformer_v2.py:177,215-221 -- */
+int tatt_rpe_gather(const float* emb, float* X, int H, int W, int C, void* stream);
+int tatt_rpe_scatter(const float* dX, float* demb, int H, int W, int C, void* stream);
+int tatt_rpe_gate_fwd(const float* GI, const float* GH, float* HALL, float* GATES, float* QPOS, int step, int N,
+                      int Wd, int Hd, int C, int Himg, void* stream);
+int tatt_rpe_gate_bwd(const float* dQPOS, const float* HALL, const float* GATES, float* DH, float* DGISUM,
+                      float* DGH, int step, int N, int Wd, int Hd, int C, int Himg, void* stream);
+
+/* ---- multi-head attention core (64 = 4 x 16, <= 32 keys): nn.MultiheadAttention as used at
+ * model/transformer_v2.py:476-478 (encoder) and 820-823 (decoder cross-attention) ----------------------- */
+int tatt_mha64_fwd(const float* Q, const float* K, const float* V, float* O, float* AW, int N, int Lq, int Lk,
+                   float pdrop, const unsigned long long* rng, unsigned long long site, void* stream);
+int tatt_mha64_bwd(const float* Q, const float* K, const float* V, const float* dO, float* dQ, float* dK, float* dV,
+                   int N, int Lq, int Lk, float pdrop, const unsigned long long* rng, unsigned long long site,
+                   void* stream);
+
+/* ---- element-wise / layout ------------------------------------------------------------------------------
+ * PReLU (tsrn.py:598,173), PixelShuffle(2)+mish (tsrn.py:1049-1053), tanh (tsrn.py:675), Dropout,
+ * MaxPool2d (stn_head.py:34-44), residual adds. */
+int tatt_axpby(const float* a, const float* b, float alpha, float beta, float* out, long long n, void* stream);
+int tatt_add_bcast_rows(const float* a, const float* b, float* out, long long rows, long long period, int cols,
+                        void* stream);
+int tatt_prelu_fwd(const float* x, const float* w, float* y, long long n, void* stream);
+int tatt_prelu_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, long long n,
+                   void* stream);
+int tatt_pixshuf2_mish_fwd(const float* in, float* out, long long nimg, int H, int W, int C, void* stream);
+int tatt_pixshuf2_mish_bwd(const float* in, const float* dout, float* din, long long nimg, int H, int W, int C,
+                           void* stream);
+int tatt_nchw_to_nhwc(const float* in, float* out, long long N, int C, int H, int W, int Cp, void* stream);
+int tatt_nhwc_to_nchw(const float* in, float* out, long long N, int C, int H, int W, int Cp, int do_tanh,
+                      void* stream);
+int tatt_tanh_bwd_nchw_to_nhwc(const float* dout, const float* out, float* dpre, long long N, int C, int H, int W,
+                               int Cp, void* stream);
+/* rng: DEVICE pointer to {seed, counter} (graph-capture safe); site: per-call-site stream id */
+int tatt_dropout(const float* x, float* y, long long n, float p, const unsigned long long* rng,
+                 unsigned long long site, void* stream);
+int tatt_rng_advance(unsigned long long* rng, void* stream);
+int tatt_relu_bwd(const float* y, const float* dy, float* dx, long long n, void* stream);
+int tatt_maxpool_fwd(const float* in, float* out, long long N, int H, int W, int C, int kh, int kw, void* stream);
+int tatt_maxpool_bwd(const float* in, const float* dout, float* din, long long N, int H, int W, int C, int kh,
+                     int kw, void* stream);
+
+/* ---- TPS grid + bilinear grid_sample: model/tps_spatial_transformer.py:97-112,10-18 -------------------- */
+int tatt_tps_sample_fwd(const float* X, const float* ctrl, const float* invK, const float* repr, float* OUT,
+                        float* SRC, int N, int H, int W, void* stream);
+int tatt_tps_sample_bwd(const float* X, const float* ctrl, const float* invK, const float* repr, const float* dOUT,
+                        float* dctrl, int N, int H, int W, void* stream);
+
+/* ---- gradient step on a flat buffer: clip_grad_norm_(0.25) + Adam, interfaces/super_resolution.py:1083-1085 */
+int tatt_sqnorm(const float* x, long long n, float* out, int zero_first, void* stream);
+int tatt_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, const float* sqnorm,
+                        float max_norm, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                        void* stream);
+
+/* ---- plumbing ------------------------------------------------------------------------------------------- */
+int tatt_memcpy_d2d(void* dst, const void* src, long long bytes, void* stream);
+int tatt_memset0(void* dst, long long bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TATT_B200_H_ */

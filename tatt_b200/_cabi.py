@@ -1,0 +1,85 @@
+"""ctypes binding of the C-ABI library (include/tatt_b200.h is the single source of truth:
+prototypes are parsed from it, so every declared symbol must be exported by the .so).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List, Tuple
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(HERE, "..", "include", "tatt_b200.h")
+LIB_PATH = os.path.join(HERE, "lib", "libtatt_b200.so")
+
+_CTYPES = {
+    "int": ctypes.c_int,
+    "long long": ctypes.c_longlong,
+    "unsigned long long": ctypes.c_ulonglong,
+    "float": ctypes.c_float,
+}
+
+
+def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[str]]]:
+    """-> {name: (return type, [arg types])} for every prototype in the header."""
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", " ", txt, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int|const char\*)\s+(tatt_\w+)\s*\(([^)]*)\)\s*;", txt):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        types = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    types.append("ptr")
+                else:
+                    t = " ".join(a.split(" ")[:-1])
+                    if t not in _CTYPES:
+                        raise RuntimeError("unknown C type %r in %s" % (a, name))
+                    types.append(t)
+        protos[name] = (ret, types)
+    return protos
+
+
+_lib = None
+_protos = None
+
+
+def lib():
+    global _lib, _protos
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "tatt_b200: C-ABI library %s not built. Run `python -m tatt_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU / PyTorch fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    _protos = parse_header()
+    for name, (ret, types) in _protos.items():
+        try:
+            fn = getattr(L, name)
+        except AttributeError as e:
+            raise RuntimeError("tatt_b200: symbol %s declared in the header is not exported" % name) from e
+        fn.restype = ctypes.c_char_p if ret != "int" else ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p if t == "ptr" else _CTYPES[t] for t in types]
+    _lib = L
+    return L
+
+
+def protos():
+    lib()
+    return _protos
+
+
+def last_error() -> str:
+    e = lib().tatt_last_error()
+    return e.decode() if e else ""
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point; non-zero -> RuntimeError(tatt_last_error())."""
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, last_error()))

@@ -1,0 +1,408 @@
+// Element-wise / layout kernels (all HBM-bound; vectorised where the layout allows).
+// Reference ops replaced: nn.PReLU (tsrn.py:598, 173), mish (tsrn.py:1061-1064), nn.PixelShuffle
+// (tsrn.py:1046), torch.tanh (tsrn.py:675), nn.Dropout (transformer_v2.py:29,455,461-462,788,795-797),
+// the NCHW<->NHWC permutes around GruBlock (tsrn.py:1076-1083) and the residual adds.
+#include "common.cuh"
+
+namespace {
+
+static int ew_blocks(long long n, int per = 256) {
+  long long b = (n + per - 1) / per;
+  if (b > 148LL * 16) b = 148LL * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define GRID_STRIDE(i, n) \
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+__global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha, float beta,
+                             float* __restrict__ out, long long n) {
+  GRID_STRIDE(i, n) out[i] = alpha * a[i] + (b ? beta * b[i] : 0.f);
+}
+__global__ void axpby4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float alpha, float beta,
+                              float4* __restrict__ out, long long n4) {
+  GRID_STRIDE(i, n4) {
+    float4 x = a[i], y = b[i];
+    out[i] = make_float4(alpha * x.x + beta * y.x, alpha * x.y + beta * y.y, alpha * x.z + beta * y.z,
+                         alpha * x.w + beta * y.w);
+  }
+}
+
+// out[r][c] = a[r][c] + b[r % period][c]   (broadcast add over the leading axis; rows of `cols`)
+__global__ void add_bcast_rows_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                      float* __restrict__ out, long long rows, long long period, int cols) {
+  long long n = rows * cols;
+  GRID_STRIDE(i, n) {
+    long long r = i / cols;
+    int c = (int)(i - r * cols);
+    out[i] = (a ? a[i] : 0.f) + b[(r % period) * cols + c];
+  }
+}
+
+__global__ void prelu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                                 long long n) {
+  const float a = w[0];
+  GRID_STRIDE(i, n) {
+    float v = x[i];
+    y[i] = v >= 0.f ? v : a * v;
+  }
+}
+// dx = dy * (x>=0 ? 1 : a) ; dw += sum dy * x * [x<0]   (torch: x > 0 ? 1 : a; equal at 0 up to dw term = 0)
+__global__ void prelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ dy, float* __restrict__ dx, float* __restrict__ dw,
+                                 long long n) {
+  __shared__ float red[8];
+  const float a = w[0];
+  float s = 0.f;
+  GRID_STRIDE(i, n) {
+    float v = x[i], g = dy[i];
+    if (v > 0.f) {
+      if (dx) dx[i] = g;
+    } else {
+      if (dx) dx[i] = a * g;
+      s = fmaf(g, v, s);
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(dw, t);
+  }
+}
+
+// in [N][H][W][4*C] -> out [N][2H][2W][C], out[n,2h+i,2w+j,c] = mish(in[n,h,w,4c+2i+j])
+__global__ void pixshuf_mish_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix_out,
+                                        int H2, int W2, int C) {
+  long long n = npix_out * C;
+  GRID_STRIDE(i, n) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int ox = (int)(p % W2);
+    long long q = p / W2;
+    int oy = (int)(q % H2);
+    long long img = q / H2;
+    int h = oy >> 1, ii = oy & 1, w = ox >> 1, jj = ox & 1;
+    long long src = (((img * (H2 >> 1) + h) * (W2 >> 1) + w) * (4LL * C)) + 4 * c + 2 * ii + jj;
+    out[i] = mish_f(in[src]);
+  }
+}
+__global__ void pixshuf_mish_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout,
+                                        float* __restrict__ din, long long npix_in, int H, int W, int C) {
+  // one thread per input element (coalesced on the 4C axis)
+  long long n = npix_in * 4LL * C;
+  GRID_STRIDE(i, n) {
+    int ch = (int)(i % (4 * C));
+    long long p = i / (4 * C);
+    int w = (int)(p % W);
+    long long q = p / W;
+    int h = (int)(q % H);
+    long long img = q / H;
+    int c = ch >> 2, ii = (ch >> 1) & 1, jj = ch & 1;
+    long long dst = (((img * (2 * H) + 2 * h + ii) * (2LL * W) + 2 * w + jj) * C) + c;
+    din[i] = dout[dst] * mish_grad(in[i]);
+  }
+}
+
+// NCHW (C real channels) -> NHWC with Cp >= C channels (zero padded)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, long long N, int C,
+                                    int HW, int Cp) {
+  long long n = N * HW * Cp;
+  GRID_STRIDE(i, n) {
+    int c = (int)(i % Cp);
+    long long p = i / Cp;
+    int hw = (int)(p % HW);
+    long long img = p / HW;
+    out[i] = c < C ? in[(img * C + c) * HW + hw] : 0.f;
+  }
+}
+// NHWC (Cp channels) -> NCHW keeping the first C channels; optional tanh
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, long long N, int C,
+                                    int HW, int Cp, int do_tanh) {
+  long long n = N * C * HW;
+  GRID_STRIDE(i, n) {
+    int hw = (int)(i % HW);
+    long long r = i / HW;
+    int c = (int)(r % C);
+    long long img = r / C;
+    float v = in[(img * HW + hw) * Cp + c];
+    out[i] = do_tanh ? tanhf(v) : v;
+  }
+}
+// d(pre)[NHWC, Cp] = dout[NCHW, C] * (1 - out^2)   (padded channels get 0)
+__global__ void tanh_bwd_nchw_to_nhwc_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                             float* __restrict__ dpre, long long N, int C, int HW, int Cp) {
+  long long n = N * HW * Cp;
+  GRID_STRIDE(i, n) {
+    int c = (int)(i % Cp);
+    long long p = i / Cp;
+    int hw = (int)(p % HW);
+    long long img = p / HW;
+    float v = 0.f;
+    if (c < C) {
+      long long s = (img * C + c) * HW + hw;
+      float o = out ? out[s] : 0.f;
+      v = dout[s] * (1.f - o * o);
+    }
+    dpre[i] = v;
+  }
+}
+
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p,
+                               const unsigned long long* __restrict__ rng, unsigned long long site) {
+  const float scale = 1.f / (1.f - p);
+  const unsigned long long seed = rng[0], offset = rng[1] * 65536ull + site;
+  long long n4 = (n + 3) >> 2;
+  GRID_STRIDE(i, n4) {
+    float4 u = philox_uniform4(seed, offset, (unsigned long long)i);
+    long long b = i << 2;
+    float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (b + k < n) y[b + k] = uu[k] >= p ? x[b + k] * scale : 0.f;
+  }
+}
+
+__global__ void relu_mask_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                     float* __restrict__ dx, long long n) {
+  GRID_STRIDE(i, n) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+// 2x2 / 1x2 max pooling, NHWC, stride == kernel
+__global__ void maxpool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, long long N, int H,
+                                   int W, int C, int kh, int kw) {
+  int Ho = H / kh, Wo = W / kw;
+  long long n = N * Ho * Wo * C;
+  GRID_STRIDE(i, n) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int ox = (int)(p % Wo);
+    long long q = p / Wo;
+    int oy = (int)(q % Ho);
+    long long img = q / Ho;
+    float m = -INFINITY;
+    for (int a = 0; a < kh; ++a)
+      for (int b = 0; b < kw; ++b) {
+        float v = in[((img * H + oy * kh + a) * W + ox * kw + b) * C + c];
+        m = v > m ? v : m;
+      }
+    out[i] = m;
+  }
+}
+__global__ void maxpool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout,
+                                   float* __restrict__ din, long long N, int H, int W, int C, int kh, int kw) {
+  int Ho = H / kh, Wo = W / kw;
+  long long n = N * Ho * Wo * C;
+  GRID_STRIDE(i, n) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int ox = (int)(p % Wo);
+    long long q = p / Wo;
+    int oy = (int)(q % Ho);
+    long long img = q / Ho;
+    float m = -INFINITY;
+    int am = 0;
+    for (int a = 0; a < kh; ++a)
+      for (int b = 0; b < kw; ++b) {
+        float v = in[((img * H + oy * kh + a) * W + ox * kw + b) * C + c];
+        if (v > m) {
+          m = v;
+          am = a * kw + b;
+        }
+      }
+    float g = dout[i];
+    for (int a = 0; a < kh; ++a)
+      for (int b = 0; b < kw; ++b)
+        din[((img * H + oy * kh + a) * W + ox * kw + b) * C + c] = (a * kw + b == am) ? g : 0.f;
+  }
+}
+
+__global__ void sqnorm_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  GRID_STRIDE(i, n) s = fmaf(x[i], x[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+
+// Fused global-norm clip + Adam on a flat fp32 buffer (super_resolution.py:1083-1085, base.py:557-558).
+// sqnorm[0] holds sum(g^2) over the whole buffer (already all-reduced and averaged grads).
+__global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, const float* __restrict__ sqnorm,
+                                 float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2,
+                                 float grad_scale) {
+  float coef = 1.f;
+  if (max_norm > 0.f) {
+    float tn = sqrtf(sqnorm[0]) * grad_scale;
+    coef = fminf(max_norm / (tn + 1e-6f), 1.f);
+  }
+  coef *= grad_scale;
+  GRID_STRIDE(i, n) {
+    float gi = g[i] * coef;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// out = alpha*a + beta*b   (b may be NULL)
+int tatt_axpby(const float* a, const float* b, float alpha, float beta, float* out, long long n, void* stream) {
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool v4 = b && (n % 4 == 0) && ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out)) & 15) == 0;
+  if (v4)
+    axpby4_kernel<<<ew_blocks(n / 4), 256, 0, st>>>((const float4*)a, (const float4*)b, alpha, beta, (float4*)out,
+                                                    n / 4);
+  else
+    axpby_kernel<<<ew_blocks(n), 256, 0, st>>>(a, b, alpha, beta, out, n);
+  TATT_LAUNCH_CHECK("axpby_kernel");
+  return 0;
+}
+
+int tatt_add_bcast_rows(const float* a, const float* b, float* out, long long rows, long long period, int cols,
+                        void* stream) {
+  if (rows <= 0) return 0;
+  add_bcast_rows_kernel<<<ew_blocks(rows * cols), 256, 0, (cudaStream_t)stream>>>(a, b, out, rows, period, cols);
+  TATT_LAUNCH_CHECK("add_bcast_rows_kernel");
+  return 0;
+}
+
+int tatt_prelu_fwd(const float* x, const float* w, float* y, long long n, void* stream) {
+  if (n <= 0) return 0;
+  prelu_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, w, y, n);
+  TATT_LAUNCH_CHECK("prelu_fwd_kernel");
+  return 0;
+}
+// dw (1 element) is zeroed here and then accumulated; dx may be NULL.
+int tatt_prelu_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, long long n,
+                   void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TATT_CUDA(cudaMemsetAsync(dw, 0, sizeof(float), st));
+  if (n <= 0) return 0;
+  prelu_bwd_kernel<<<ew_blocks(n, 1024), 256, 0, st>>>(x, w, dy, dx, dw, n);
+  TATT_LAUNCH_CHECK("prelu_bwd_kernel");
+  return 0;
+}
+
+int tatt_pixshuf2_mish_fwd(const float* in, float* out, long long nimg, int H, int W, int C, void* stream) {
+  long long npix_out = nimg * 4LL * H * W;
+  if (npix_out <= 0) return 0;
+  pixshuf_mish_fwd_kernel<<<ew_blocks(npix_out * C), 256, 0, (cudaStream_t)stream>>>(in, out, npix_out, 2 * H,
+                                                                                     2 * W, C);
+  TATT_LAUNCH_CHECK("pixshuf_mish_fwd_kernel");
+  return 0;
+}
+int tatt_pixshuf2_mish_bwd(const float* in, const float* dout, float* din, long long nimg, int H, int W, int C,
+                           void* stream) {
+  long long npix_in = nimg * (long long)H * W;
+  if (npix_in <= 0) return 0;
+  pixshuf_mish_bwd_kernel<<<ew_blocks(npix_in * 4 * C), 256, 0, (cudaStream_t)stream>>>(in, dout, din, npix_in, H,
+                                                                                        W, C);
+  TATT_LAUNCH_CHECK("pixshuf_mish_bwd_kernel");
+  return 0;
+}
+
+int tatt_nchw_to_nhwc(const float* in, float* out, long long N, int C, int H, int W, int Cp, void* stream) {
+  long long n = N * H * W * Cp;
+  if (n <= 0) return 0;
+  nchw_to_nhwc_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(in, out, N, C, H * W, Cp);
+  TATT_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return 0;
+}
+int tatt_nhwc_to_nchw(const float* in, float* out, long long N, int C, int H, int W, int Cp, int do_tanh,
+                      void* stream) {
+  long long n = N * C * H * W;
+  if (n <= 0) return 0;
+  nhwc_to_nchw_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(in, out, N, C, H * W, Cp, do_tanh);
+  TATT_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return 0;
+}
+int tatt_tanh_bwd_nchw_to_nhwc(const float* dout, const float* out, float* dpre, long long N, int C, int H, int W,
+                               int Cp, void* stream) {
+  long long n = N * H * W * Cp;
+  if (n <= 0) return 0;
+  tanh_bwd_nchw_to_nhwc_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(dout, out, dpre, N, C, H * W, Cp);
+  TATT_LAUNCH_CHECK("tanh_bwd_nchw_to_nhwc_kernel");
+  return 0;
+}
+
+__global__ void rng_advance_kernel(unsigned long long* rng) { rng[1] += 1ull; }
+
+// y = x * keep / (1-p); the same call on dy (same rng snapshot / site) is the backward.
+// rng: device pointer to {seed, counter}; the mask of element i is Philox(seed; i, counter*65536+site).
+int tatt_dropout(const float* x, float* y, long long n, float p, const unsigned long long* rng,
+                 unsigned long long site, void* stream) {
+  TATT_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
+  if (n <= 0) return 0;
+  dropout_kernel<<<ew_blocks((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, rng, site);
+  TATT_LAUNCH_CHECK("dropout_kernel");
+  return 0;
+}
+int tatt_rng_advance(unsigned long long* rng, void* stream) {
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng);
+  TATT_LAUNCH_CHECK("rng_advance_kernel");
+  return 0;
+}
+
+int tatt_relu_bwd(const float* y, const float* dy, float* dx, long long n, void* stream) {
+  if (n <= 0) return 0;
+  relu_mask_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n);
+  TATT_LAUNCH_CHECK("relu_mask_bwd_kernel");
+  return 0;
+}
+
+int tatt_maxpool_fwd(const float* in, float* out, long long N, int H, int W, int C, int kh, int kw, void* stream) {
+  long long n = N * (H / kh) * (W / kw) * C;
+  if (n <= 0) return 0;
+  maxpool_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(in, out, N, H, W, C, kh, kw);
+  TATT_LAUNCH_CHECK("maxpool_fwd_kernel");
+  return 0;
+}
+int tatt_maxpool_bwd(const float* in, const float* dout, float* din, long long N, int H, int W, int C, int kh,
+                     int kw, void* stream) {
+  TATT_REQUIRE(H % kh == 0 && W % kw == 0, "maxpool_bwd: H,W must be divisible by the window");
+  long long n = N * (H / kh) * (W / kw) * C;
+  if (n <= 0) return 0;
+  maxpool_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(in, dout, din, N, H, W, C, kh, kw);
+  TATT_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return 0;
+}
+
+// out[0] (+)= sum x^2
+int tatt_sqnorm(const float* x, long long n, float* out, int zero_first, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zero_first) TATT_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  if (n <= 0) return 0;
+  sqnorm_kernel<<<ew_blocks(n, 2048), 256, 0, st>>>(x, n, out);
+  TATT_LAUNCH_CHECK("sqnorm_kernel");
+  return 0;
+}
+
+int tatt_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, const float* sqnorm,
+                        float max_norm, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                        void* stream) {
+  if (n <= 0) return 0;
+  float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_clip_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sqnorm, max_norm, lr, beta1,
+                                                                   beta2, eps, bc1, bc2, grad_scale);
+  TATT_LAUNCH_CHECK("adam_clip_kernel");
+  return 0;
+}
+
+}  // extern "C"

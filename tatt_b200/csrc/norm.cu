@@ -1,0 +1,312 @@
+// BatchNorm (channels-last, batch statistics over all rows) and LayerNorm(64) kernels, fwd + bwd.
+// Reference ops replaced: nn.BatchNorm2d/1d (model/tsrn.py:878,886,612; model/stn_head.py:19,51)
+// and nn.LayerNorm(64) (model/transformer_v2.py:460-461, 792-794, 166).
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- BatchNorm statistics
+// X[P][C]; per-channel sum and sum of squares -> double accumulators acc[2*C].
+__global__ void bn_stats_kernel(const float* __restrict__ X, long long P, int C, int rows_per_cta,
+                                double* __restrict__ acc) {
+  __shared__ float red[2][4][64];
+  const int lane = threadIdx.x & 63;
+  const int ty = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + lane;
+  long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > P) r1 = P;
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    for (long long r = r0 + ty; r < r1; r += 4) {
+      float v = X[r * C + c];
+      s += v;
+      q = fmaf(v, v, q);
+    }
+  }
+  red[0][ty][lane] = s;
+  red[1][ty][lane] = q;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float ts = red[0][0][lane] + red[0][1][lane] + red[0][2][lane] + red[0][3][lane];
+    float tq = red[1][0][lane] + red[1][1][lane] + red[1][2][lane] + red[1][3][lane];
+    atomicAdd(acc + c, (double)ts);
+    atomicAdd(acc + C + c, (double)tq);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ acc, long long P, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = acc[c] / (double)P;
+  double var = acc[C + c] / (double)P - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+  }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
+                                     float* __restrict__ mean, float* __restrict__ invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rm[c];
+  invstd[c] = 1.f / sqrtf(rv[c] + eps);
+}
+
+// Y = act(X * scale + shift)   (C % 4 == 0)
+__global__ void bn_apply_kernel(const float* __restrict__ X, float* __restrict__ Y, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int act, long long total4, int C4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4;
+    float4 x = reinterpret_cast<const float4*>(X)[i];
+    float4 m = *reinterpret_cast<const float4*>(mean + c);
+    float4 is = *reinterpret_cast<const float4*>(invstd + c);
+    float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    float4 b = *reinterpret_cast<const float4*>(beta + c);
+    float4 y;
+    y.x = act_fwd((x.x - m.x) * is.x * g.x + b.x, act);
+    y.y = act_fwd((x.y - m.y) * is.y * g.y + b.y, act);
+    y.z = act_fwd((x.z - m.z) * is.z * g.z + b.z, act);
+    y.w = act_fwd((x.w - m.w) * is.w * g.w + b.w, act);
+    reinterpret_cast<float4*>(Y)[i] = y;
+  }
+}
+
+// acc[c] += sum dz, acc[C+c] += sum dz * xhat   with dz = dY * act'(z)
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ X, const float* __restrict__ dY,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                     long long P, int C, int rows_per_cta, double* __restrict__ acc) {
+  __shared__ float red[2][4][64];
+  const int lane = threadIdx.x & 63;
+  const int ty = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + lane;
+  long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > P) r1 = P;
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    float m = mean[c], is = invstd[c], g = gamma[c], b = beta[c];
+    for (long long r = r0 + ty; r < r1; r += 4) {
+      float xh = (X[r * C + c] - m) * is;
+      float dz = dY[r * C + c];
+      if (act != ACT_NONE) dz *= act_grad(xh * g + b, act);
+      s += dz;
+      q = fmaf(dz, xh, q);
+    }
+  }
+  red[0][ty][lane] = s;
+  red[1][ty][lane] = q;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float ts = red[0][0][lane] + red[0][1][lane] + red[0][2][lane] + red[0][3][lane];
+    float tq = red[1][0][lane] + red[1][1][lane] + red[1][2][lane] + red[1][3][lane];
+    atomicAdd(acc + c, (double)ts);
+    atomicAdd(acc + C + c, (double)tq);
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ acc, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbeta[c] = (float)acc[c];
+  dgamma[c] = (float)acc[C + c];
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ X, const float* __restrict__ dY,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int act,
+                                    int training, float invP, long long total, int C, float* __restrict__ dX) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float m = mean[c], is = invstd[c], g = gamma[c];
+    float xh = (X[i] - m) * is;
+    float dz = dY[i];
+    if (act != ACT_NONE) dz *= act_grad(xh * g + beta[c], act);
+    float v;
+    if (training)
+      v = g * is * (dz - dbeta[c] * invP - xh * dgamma[c] * invP);
+    else
+      v = g * is * dz;
+    dX[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm over 64 channels
+// one warp per row; lane owns channels lane and lane+32
+__global__ void ln_fwd_kernel(const float* __restrict__ X, const float* __restrict__ R,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ Y, float* __restrict__ S, float* __restrict__ mean,
+                              float* __restrict__ rstd, long long P, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float g0 = gamma[lane], g1 = gamma[lane + 32], b0 = beta[lane], b1 = beta[lane + 32];
+  for (long long r = warp; r < P; r += nwarp) {
+    float v0 = X[r * 64 + lane], v1 = X[r * 64 + lane + 32];
+    if (R) {
+      v0 += R[r * 64 + lane];
+      v1 += R[r * 64 + lane + 32];
+    }
+    if (S) {
+      S[r * 64 + lane] = v0;
+      S[r * 64 + lane + 32] = v1;
+    }
+    float m = warp_sum(v0 + v1) * (1.f / 64.f);
+    float d0 = v0 - m, d1 = v1 - m;
+    float var = warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f);
+    float rs = 1.f / sqrtf(var + eps);
+    Y[r * 64 + lane] = d0 * rs * g0 + b0;
+    Y[r * 64 + lane + 32] = d1 * rs * g1 + b1;
+    if (lane == 0 && mean) {
+      mean[r] = m;
+      rstd[r] = rs;
+    }
+  }
+}
+
+__global__ void ln_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ S,
+                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                              const float* __restrict__ gamma, float* __restrict__ dS,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta, long long P) {
+  __shared__ float red[2][8][64];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float g0 = gamma[lane], g1 = gamma[lane + 32];
+  float ag0 = 0.f, ag1 = 0.f, ab0 = 0.f, ab1 = 0.f;
+  for (long long r = warp; r < P; r += nwarp) {
+    float m = mean[r], rs = rstd[r];
+    float xh0 = (S[r * 64 + lane] - m) * rs, xh1 = (S[r * 64 + lane + 32] - m) * rs;
+    float dy0 = dY[r * 64 + lane], dy1 = dY[r * 64 + lane + 32];
+    ag0 = fmaf(dy0, xh0, ag0);
+    ag1 = fmaf(dy1, xh1, ag1);
+    ab0 += dy0;
+    ab1 += dy1;
+    float w0 = dy0 * g0, w1 = dy1 * g1;
+    float c1 = warp_sum(w0 + w1) * (1.f / 64.f);
+    float c2 = warp_sum(w0 * xh0 + w1 * xh1) * (1.f / 64.f);
+    dS[r * 64 + lane] = rs * (w0 - c1 - xh0 * c2);
+    dS[r * 64 + lane + 32] = rs * (w1 - c1 - xh1 * c2);
+  }
+  red[0][wib][lane] = ag0;
+  red[0][wib][lane + 32] = ag1;
+  red[1][wib][lane] = ab0;
+  red[1][wib][lane + 32] = ab1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[which][w][c];
+    atomicAdd((which == 0 ? dgamma : dbeta) + c, t);
+  }
+}
+
+static int ew_blocks(long long n, int per = 256) {
+  long long b = (n + per - 1) / per;
+  if (b > 148LL * 16) b = 148LL * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Batch statistics of X[P][C] (biased variance) -> mean/invstd; optional running-stat update with
+// the unbiased variance (torch semantics).  ws: >= 2*C doubles of scratch.
+int tatt_bn_stats(const float* X, long long P, int C, float eps, float momentum, float* mean, float* invstd,
+                  float* running_mean, float* running_var, void* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TATT_REQUIRE(P >= 1 && C >= 1, "bn_stats: empty input");
+  TATT_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
+  int rows = 128;
+  if (P > 128LL * 4096) rows = (int)((P + 4095) / 4096);
+  dim3 grid(ceil_div(P, rows), ceil_div(C, 64));
+  bn_stats_kernel<<<grid, 256, 0, st>>>(X, P, C, rows, (double*)ws);
+  TATT_LAUNCH_CHECK("bn_stats_kernel");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)ws, P, C, eps, momentum, mean, invstd,
+                                                       running_mean, running_var);
+  TATT_LAUNCH_CHECK("bn_finalize_kernel");
+  return 0;
+}
+
+int tatt_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
+                       float* invstd, void* stream) {
+  bn_eval_stats_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, eps, C,
+                                                                            mean, invstd);
+  TATT_LAUNCH_CHECK("bn_eval_stats_kernel");
+  return 0;
+}
+
+int tatt_bn_apply_fwd(const float* X, float* Y, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, int act, long long P, int C, void* stream) {
+  TATT_REQUIRE(C % 4 == 0, "bn_apply: C must be a multiple of 4");
+  long long total4 = P * C / 4;
+  if (total4 == 0) return 0;
+  bn_apply_kernel<<<ew_blocks(total4), 256, 0, (cudaStream_t)stream>>>(X, Y, mean, invstd, gamma, beta, act,
+                                                                       total4, C / 4);
+  TATT_LAUNCH_CHECK("bn_apply_kernel");
+  return 0;
+}
+
+// dgamma/dbeta (with the activation's backward fused) then dX.  ws: >= 2*C doubles.
+int tatt_bn_bwd(const float* X, const float* dY, const float* mean, const float* invstd, const float* gamma,
+                const float* beta, int act, int training, long long P, int C, float* dX, float* dgamma,
+                float* dbeta, void* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TATT_REQUIRE(P >= 1 && C >= 1, "bn_bwd: empty input");
+  TATT_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
+  int rows = 128;
+  if (P > 128LL * 4096) rows = (int)((P + 4095) / 4096);
+  dim3 grid(ceil_div(P, rows), ceil_div(C, 64));
+  bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(X, dY, mean, invstd, gamma, beta, act, P, C, rows, (double*)ws);
+  TATT_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)ws, C, dgamma, dbeta);
+  TATT_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  if (dX) {
+    long long total = P * C;
+    bn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(X, dY, mean, invstd, gamma, beta, dgamma, dbeta, act,
+                                                          training, 1.f / (float)P, total, C, dX);
+    TATT_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  }
+  return 0;
+}
+
+// Y = LN(X + R) over 64 channels; optionally stores S = X + R, mean, rstd for the backward.
+int tatt_layernorm64_fwd(const float* X, const float* R, const float* gamma, const float* beta, float* Y, float* S,
+                         float* mean, float* rstd, long long P, float eps, void* stream) {
+  if (P <= 0) return 0;
+  ln_fwd_kernel<<<ew_blocks(P, 8), 256, 0, (cudaStream_t)stream>>>(X, R, gamma, beta, Y, S, mean, rstd, P, eps);
+  TATT_LAUNCH_CHECK("ln_fwd_kernel");
+  return 0;
+}
+
+// dS (grad wrt the pre-norm sum), dgamma/dbeta (zeroed here, then accumulated).
+int tatt_layernorm64_bwd(const float* dY, const float* S, const float* mean, const float* rstd, const float* gamma,
+                         float* dS, float* dgamma, float* dbeta, long long P, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TATT_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * 64, st));
+  TATT_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * 64, st));
+  if (P <= 0) return 0;
+  int blocks = ew_blocks(P, 8 * 16);
+  ln_bwd_kernel<<<blocks, 256, 0, st>>>(dY, S, mean, rstd, gamma, dS, dgamma, dbeta, P);
+  TATT_LAUNCH_CHECK("ln_bwd_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+"""Tensor-level wrappers over the C-ABI (allocation + pointer plumbing only; every FLOP runs in the
+hand-written CUDA kernels of tatt_b200/csrc).  All tensors are fp32 CUDA tensors; feature maps are
+channels-last [N,H,W,C]; "rows" tensors are [P, C] with unit inner stride."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+Tensor = torch.Tensor
+ACT_NONE, ACT_RELU, ACT_MISH = 0, 1, 2
+F_ACCUM, F_RELU, F_SPLITK, F_ZEROC = 1, 2, 4, 64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: Tensor, name: str = "tensor") -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("tatt_b200: %s must be a CUDA tensor (the hot path has no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("tatt_b200: %s must be float32, got %s" % (name, t.dtype))
+    return t
+
+
+def _rows(t: Tensor) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a 2-D tensor with unit inner stride."""
+    assert t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1), (t.shape, t.stride())
+    return t.shape[0], t.shape[1], (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
+
+
+def empty(*shape, like: Tensor) -> Tensor:
+    return torch.empty(*shape, dtype=torch.float32, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm(amode: int, bmode: int, A: Tensor, lda: int, B: Tensor, ldb: int, C: Tensor, ldc: int,
+         bias: Optional[Tensor], M: int, N: int, K: int, flags: int = 0, batch: int = 1, sA: int = 0, sB: int = 0,
+         sC: int = 0, sBias: int = 0) -> None:
+    _cabi.call("tatt_gemm", amode, bmode, _p(A), lda, _p(B), ldb, _p(C), ldc, _p(bias), M, N, K, batch, sA, sB,
+               sC, sBias, flags, _stream())
+
+
+def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], out: Optional[Tensor] = None, accumulate: bool = False,
+               relu: bool = False) -> Tensor:
+    """out[M,N] (=|+=) x[M,K] @ w[N,K]^T + b"""
+    M, K, ldx = _rows(x)
+    N, K2, ldw = _rows(w)
+    assert K == K2, (x.shape, w.shape)
+    if out is None:
+        out = empty(M, N, like=x)
+    _, _, ldo = _rows(out)
+    gemm(0, 1, x, ldx, w, ldw, out, ldo, b, M, N, K, (F_ACCUM if accumulate else 0) | (F_RELU if relu else 0))
+    return out
+
+
+def linear_bwd_data(dy: Tensor, w: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """out[M,K] (=|+=) dy[M,N] @ w[N,K]"""
+    M, N, lddy = _rows(dy)
+    N2, K, ldw = _rows(w)
+    assert N == N2, (dy.shape, w.shape)
+    if out is None:
+        out = empty(M, K, like=dy)
+    _, _, ldo = _rows(out)
+    gemm(0, 0, dy, lddy, w, ldw, out, ldo, None, M, K, N, F_ACCUM if accumulate else 0)
+    return out
+
+
+def linear_bwd_weight(dy: Tensor, x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """out[N,K] += dy[M,N]^T @ x[M,K]  (split-K atomics; `out` must be zero-filled if given)"""
+    M, N, lddy = _rows(dy)
+    M2, K, ldx = _rows(x)
+    assert M == M2, (dy.shape, x.shape)
+    flags = F_SPLITK
+    if out is None:
+        out = empty(N, K, like=dy)
+        flags |= F_ZEROC
+    _, _, ldo = _rows(out)
+    gemm(1, 0, dy, lddy, x, ldx, out, ldo, None, N, K, M, flags)
+    return out
+
+
+def colsum(x: Tensor, out: Optional[Tensor] = None, zero_first: bool = True) -> Tensor:
+    P, C, ldx = _rows(x)
+    if out is None:
+        out = empty(C, like=x)
+    _cabi.call("tatt_colsum", _p(x), ldx, _p(out), P, C, 1 if zero_first else 0, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ conv
+def _pad4(c: int) -> int:
+    return (c + 3) // 4 * 4
+
+
+def conv_pack(w: Tensor, cin_p: int, cout_p: int, flip: bool) -> Tensor:
+    co, ci, kh, kw = w.shape
+    wt = empty(kh * kw * (cout_p if flip else cin_p), (cin_p if flip else cout_p), like=w)
+    _cabi.call("tatt_conv_weight_pack", _p(w.contiguous()), _p(wt), co, ci, kh, kw, cin_p, cout_p, 1 if flip else 0,
+               _stream())
+    return wt
+
+
+def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int) -> Tensor:
+    """x [N,H,W,CinP] (CinP >= w.shape[1], multiple of 4) -> y [N,H,W,CoutP]"""
+    n, h, wd, cin_p = x.shape
+    co, ci, kh, kw = w.shape
+    cout_p = _pad4(co)
+    wt = conv_pack(w, cin_p, cout_p, False)
+    if b is not None and cout_p != co:
+        bp = torch.zeros(cout_p, dtype=torch.float32, device=x.device)
+        bp[:co].copy_(b)
+        b = bp
+    y = empty(n, h, wd, cout_p, like=x)
+    _cabi.call("tatt_conv2d_igemm", _p(x), _p(wt), _p(b), _p(y), n, h, wd, cin_p, cout_p, kh, kw, pad, pad, 0,
+               _stream())
+    return y
+
+
+def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True, need_dw: bool = True,
+               has_bias: bool = True):
+    """-> (dx [N,H,W,CinP] | None, dW [Cout,Cin,KH,KW] | None, db [Cout] | None)"""
+    n, h, wd, cin_p = x.shape
+    co, ci, kh, kw = w.shape
+    cout_p = dy.shape[-1]
+    dx = dw = db = None
+    if need_dw:
+        dwt = empty(kh * kw * cin_p, cout_p, like=x)
+        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dy), _p(dwt), n, h, wd, cin_p, cout_p, kh, kw, pad, pad, _stream())
+        dw = empty(co, ci, kh, kw, like=x)
+        _cabi.call("tatt_conv_weight_unpack_grad", _p(dwt), _p(dw), co, ci, kh, kw, cin_p, cout_p, _stream())
+        if has_bias:
+            db = colsum(dy.view(-1, cout_p))[:co]
+    if need_dx:
+        wb = conv_pack(w, cin_p, cout_p, True)
+        dx = empty(n, h, wd, cin_p, like=x)
+        _cabi.call("tatt_conv2d_igemm", _p(dy), _p(wb), None, _p(dx), n, h, wd, cout_p, cin_p, kh, kw,
+                   kh - 1 - pad, kw - 1 - pad, 0, _stream())
+    return dx, dw, db
+
+
+# ------------------------------------------------------------------------------------------ norms
+def bn_stats(x2: Tensor, eps: float, momentum: float, running_mean: Optional[Tensor],
+             running_var: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    P, C = x2.shape
+    st = empty(2, C, like=x2)
+    ws = torch.empty(2 * C, dtype=torch.float64, device=x2.device)
+    _cabi.call("tatt_bn_stats", _p(x2), P, C, eps, momentum, _p(st[0]), _p(st[1]), _p(running_mean),
+               _p(running_var), _p(ws), _stream())
+    return st[0], st[1]
+
+
+def bn_eval_stats(running_mean: Tensor, running_var: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+    C = running_mean.numel()
+    st = empty(2, C, like=running_mean)
+    _cabi.call("tatt_bn_eval_stats", _p(running_mean), _p(running_var), eps, C, _p(st[0]), _p(st[1]), _stream())
+    return st[0], st[1]
+
+
+def bn_apply(x2: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, act: int) -> Tensor:
+    P, C = x2.shape
+    y = torch.empty_like(x2)
+    _cabi.call("tatt_bn_apply_fwd", _p(x2), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), act, P, C, _stream())
+    return y
+
+
+def bn_bwd(x2: Tensor, dy2: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, act: int,
+           training: bool, need_dx: bool = True):
+    P, C = x2.shape
+    dx = torch.empty_like(x2) if need_dx else None
+    dg = empty(2, C, like=x2)
+    ws = torch.empty(2 * C, dtype=torch.float64, device=x2.device)
+    _cabi.call("tatt_bn_bwd", _p(x2), _p(dy2), _p(mean), _p(invstd), _p(gamma), _p(beta), act, 1 if training else 0,
+               P, C, _p(dx), _p(dg[0]), _p(dg[1]), _p(ws), _stream())
+    return dx, dg[0], dg[1]
+
+
+def layernorm_fwd(x2: Tensor, r2: Optional[Tensor], gamma: Tensor, beta: Tensor, save: bool):
+    """y = LN(x + r); returns (y, S=x+r | None, stats[2,P] | None)"""
+    P, C = x2.shape
+    assert C == 64
+    y = torch.empty_like(x2)
+    S = torch.empty_like(x2) if (save and r2 is not None) else None
+    st = empty(2, P, like=x2) if save else None
+    _cabi.call("tatt_layernorm64_fwd", _p(x2), _p(r2), _p(gamma), _p(beta), _p(y), _p(S),
+               _p(st[0]) if save else None, _p(st[1]) if save else None, P, 1e-5, _stream())
+    if save and r2 is None:
+        S = x2
+    return y, S, st
+
+
+def layernorm_bwd(dy2: Tensor, S: Tensor, st: Tensor, gamma: Tensor):
+    P, C = dy2.shape
+    dS = torch.empty_like(dy2)
+    dgb = empty(2, 64, like=dy2)
+    _cabi.call("tatt_layernorm64_bwd", _p(dy2), _p(S), _p(st[0]), _p(st[1]), _p(gamma), _p(dS), _p(dgb[0]),
+               _p(dgb[1]), P, _stream())
+    return dS, dgb[0], dgb[1]
+
+
+# ------------------------------------------------------------------------------------------ GRU(32)
+def gru32_scan_fwd(gi: Tensor, whh: Tensor, bhh: Tensor, nseq: int, T: int, s_inner: int, outer: int, inner: int,
+                   tstride: int, save: bool):
+    P = gi.shape[0]
+    out = empty(P, 64, like=gi)
+    gates = empty(P, 320, like=gi) if save else None
+    _cabi.call("tatt_gru32_scan_fwd", _p(gi), _p(whh), _p(bhh), _p(out), _p(gates), nseq, T, s_inner, outer, inner,
+               tstride, _stream())
+    return out, gates
+
+
+def gru32_scan_bwd(dout: Tensor, gates: Tensor, whh: Tensor, nseq: int, T: int, s_inner: int, outer: int,
+                   inner: int, tstride: int):
+    P = dout.shape[0]
+    dgi = empty(P, 192, like=dout)
+    dgh = empty(P, 192, like=dout)
+    _cabi.call("tatt_gru32_scan_bwd", _p(dout), _p(gates), _p(whh), _p(dgi), _p(dgh), nseq, T, s_inner, outer,
+               inner, tstride, _stream())
+    return dgi, dgh
+
+
+# ------------------------------------------------------------------------------------------ attention
+def mha_fwd(q: Tensor, k: Tensor, v: Tensor, N: int, Lq: int, Lk: int, need_weights: bool, pdrop: float,
+            rng: Optional[Tensor], site: int):
+    o = torch.empty_like(q)
+    aw = empty(N, Lq, Lk, like=q) if need_weights else None
+    _cabi.call("tatt_mha64_fwd", _p(q), _p(k), _p(v), _p(o), _p(aw), N, Lq, Lk, pdrop, _p(rng), site, _stream())
+    return o, aw
+
+
+def mha_bwd(q: Tensor, k: Tensor, v: Tensor, do: Tensor, N: int, Lq: int, Lk: int, pdrop: float,
+            rng: Optional[Tensor], site: int):
+    dq = torch.empty_like(q)
+    dk = torch.empty_like(k)
+    dv = torch.empty_like(v)
+    _cabi.call("tatt_mha64_bwd", _p(q), _p(k), _p(v), _p(do), _p(dq), _p(dk), _p(dv), N, Lq, Lk, pdrop, _p(rng),
+               site, _stream())
+    return dq, dk, dv
+
+
+# ------------------------------------------------------------------------------------------ element-wise
+def axpby(a: Tensor, b: Optional[Tensor], alpha: float = 1.0, beta: float = 1.0, out: Optional[Tensor] = None):
+    if out is None:
+        out = torch.empty_like(a)
+    _cabi.call("tatt_axpby", _p(a), _p(b), alpha, beta, _p(out), a.numel(), _stream())
+    return out
+
+
+def add(a: Tensor, b: Tensor) -> Tensor:
+    return axpby(a, b, 1.0, 1.0)
+
+
+def add_bcast_rows(a: Optional[Tensor], b: Tensor, rows: int, period: int, cols: int) -> Tensor:
+    out = empty(rows, cols, like=b)
+    _cabi.call("tatt_add_bcast_rows", _p(a), _p(b), _p(out), rows, period, cols, _stream())
+    return out
+
+
+def prelu_fwd(x: Tensor, w: Tensor) -> Tensor:
+    y = torch.empty_like(x)
+    _cabi.call("tatt_prelu_fwd", _p(x), _p(w), _p(y), x.numel(), _stream())
+    return y
+
+
+def prelu_bwd(x: Tensor, w: Tensor, dy: Tensor, need_dx: bool = True):
+    dx = torch.empty_like(x) if need_dx else None
+    dw = empty(1, like=x)
+    _cabi.call("tatt_prelu_bwd", _p(x), _p(w), _p(dy), _p(dx), _p(dw), x.numel(), _stream())
+    return dx, dw
+
+
+def dropout(x: Tensor, p: float, rng: Tensor, site: int) -> Tensor:
+    y = torch.empty_like(x)
+    _cabi.call("tatt_dropout", _p(x), _p(y), x.numel(), p, _p(rng), site, _stream())
+    return y
+
+
+def relu_bwd(y: Tensor, dy: Tensor) -> Tensor:
+    dx = torch.empty_like(dy)
+    _cabi.call("tatt_relu_bwd", _p(y), _p(dy), _p(dx), y.numel(), _stream())
+    return dx
+
+
+def nchw_to_nhwc(x: Tensor, cp: int) -> Tensor:
+    n, c, h, w = x.shape
+    out = empty(n, h, w, cp, like=x)
+    _cabi.call("tatt_nchw_to_nhwc", _p(x), _p(out), n, c, h, w, cp, _stream())
+    return out
+
+
+def nhwc_to_nchw(x: Tensor, c: int, do_tanh: bool = False) -> Tensor:
+    n, h, w, cp = x.shape
+    out = empty(n, c, h, w, like=x)
+    _cabi.call("tatt_nhwc_to_nchw", _p(x), _p(out), n, c, h, w, cp, 1 if do_tanh else 0, _stream())
+    return out
+
+
+def tanh_bwd_to_nhwc(dout: Tensor, out: Tensor, cp: int) -> Tensor:
+    n, c, h, w = dout.shape
+    dpre = empty(n, h, w, cp, like=dout)
+    _cabi.call("tatt_tanh_bwd_nchw_to_nhwc", _p(dout), _p(out), _p(dpre), n, c, h, w, cp, _stream())
+    return dpre
+
+
+def pixshuf2_mish_fwd(x: Tensor) -> Tensor:
+    n, h, w, c4 = x.shape
+    out = empty(n, 2 * h, 2 * w, c4 // 4, like=x)
+    _cabi.call("tatt_pixshuf2_mish_fwd", _p(x), _p(out), n, h, w, c4 // 4, _stream())
+    return out
+
+
+def pixshuf2_mish_bwd(x: Tensor, dout: Tensor) -> Tensor:
+    n, h, w, c4 = x.shape
+    din = torch.empty_like(x)
+    _cabi.call("tatt_pixshuf2_mish_bwd", _p(x), _p(dout), _p(din), n, h, w, c4 // 4, _stream())
+    return din
+
+
+def maxpool_fwd(x: Tensor, kh: int, kw: int) -> Tensor:
+    n, h, w, c = x.shape
+    out = empty(n, h // kh, w // kw, c, like=x)
+    _cabi.call("tatt_maxpool_fwd", _p(x), _p(out), n, h, w, c, kh, kw, _stream())
+    return out
+
+
+def maxpool_bwd(x: Tensor, dout: Tensor, kh: int, kw: int) -> Tensor:
+    n, h, w, c = x.shape
+    din = torch.empty_like(x)
+    _cabi.call("tatt_maxpool_bwd", _p(x), _p(dout), _p(din), n, h, w, c, kh, kw, _stream())
+    return din
+
+
+def tps_sample_fwd(x: Tensor, ctrl: Tensor, invk: Tensor, repr_: Tensor, want_src: bool = False):
+    n, h, w, c = x.shape
+    assert c == 4
+    out = torch.empty_like(x)
+    src = empty(n, h * w, 2, like=x) if want_src else None
+    _cabi.call("tatt_tps_sample_fwd", _p(x), _p(ctrl), _p(invk), _p(repr_), _p(out), _p(src), n, h, w, _stream())
+    return out, src
+
+
+def tps_sample_bwd(x: Tensor, ctrl: Tensor, invk: Tensor, repr_: Tensor, dout: Tensor) -> Tensor:
+    n, h, w, c = x.shape
+    dctrl = torch.empty_like(ctrl)
+    _cabi.call("tatt_tps_sample_bwd", _p(x), _p(ctrl), _p(invk), _p(repr_), _p(dout), _p(dctrl), n, h, w, _stream())
+    return dctrl
+
+
+def memcpy(dst: Tensor, src: Tensor) -> None:
+    assert dst.numel() * dst.element_size() == src.numel() * src.element_size()
+    _cabi.call("tatt_memcpy_d2d", _p(dst), _p(src), src.numel() * src.element_size(), _stream())
+
+
+def zeros(*shape, like: Tensor) -> Tensor:
+    t = torch.empty(*shape, dtype=torch.float32, device=like.device)
+    _cabi.call("tatt_memset0", _p(t), t.numel() * 4, _stream())
+    return t
+
+
+# ------------------------------------------------------------------------------------------ RNG state
+class DeviceRNG:
+    """{seed, counter} in device memory so dropout is CUDA-graph safe.  `snapshot()` copies the state
+    for one forward call (its backward re-derives the same masks) and advances the counter."""
+    _per_device = {}
+
+    def __init__(self, device: torch.device, seed: int):
+        self.state = torch.tensor([seed & ((1 << 63) - 1), 0], dtype=torch.int64, device=device)
+
+    @classmethod
+    def get(cls, device: torch.device) -> "DeviceRNG":
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        if key not in cls._per_device:
+            cls._per_device[key] = DeviceRNG(device, torch.initial_seed())
+        return cls._per_device[key]
+
+    @classmethod
+    def manual_seed(cls, seed: int) -> None:
+        for r in cls._per_device.values():
+            r.state.copy_(torch.tensor([seed & ((1 << 63) - 1), 0], dtype=torch.int64))
+
+    def snapshot(self) -> Tensor:
+        snap = torch.empty_like(self.state)
+        _cabi.call("tatt_memcpy_d2d", _p(snap), _p(self.state), 16, _stream())
+        _cabi.call("tatt_rng_advance", _p(self.state), _stream())
+        return snap

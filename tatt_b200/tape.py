@@ -1,0 +1,336 @@
+"""A minimal reverse-mode tape over raw CUDA tensors.
+
+Each method runs the forward through the C-ABI kernels (tatt_b200.ops) and, when recording, appends a
+closure that turns the gradient of its output into gradients of its inputs -- again only C-ABI calls.
+Stages (tatt_b200/stages.py) build one Tape per autograd.Function call; torch.autograd only sees the
+stage boundary.  Gradients are keyed by id(tensor); closures keep every keyed tensor alive."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+class Tape:
+    def __init__(self, record: bool):
+        self.record = record
+        self._ops: List = []
+        self._g: Dict[int, Tensor] = {}
+        self._keep: List[Tensor] = []
+
+    # ------------------------------------------------------------------ gradient bookkeeping
+    def grad(self, t: Tensor) -> Optional[Tensor]:
+        return self._g.get(id(t))
+
+    def add_grad(self, t: Tensor, g: Optional[Tensor]) -> None:
+        if g is None:
+            return
+        k = id(t)
+        if k in self._g:
+            self._g[k] = ops.add(self._g[k], g.reshape(self._g[k].shape))
+        else:
+            self._g[k] = g
+            self._keep.append(t)
+
+    def seed(self, t: Tensor, g: Optional[Tensor]) -> None:
+        if g is not None:
+            self.add_grad(t, g.contiguous().reshape(t.shape))
+
+    def backward(self) -> None:
+        for fn in reversed(self._ops):
+            fn()
+
+    def _push(self, fn) -> None:
+        if self.record:
+            self._ops.append(fn)
+
+    # ------------------------------------------------------------------ dense layers
+    def linear(self, x: Tensor, W: Tensor, b: Optional[Tensor], relu: bool = False) -> Tensor:
+        """x [M,K] @ W[N,K]^T + b (optionally ReLU)"""
+        y = ops.linear_fwd(x, W, b, relu=relu)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is None:
+                return
+            if relu:
+                dy = ops.relu_bwd(y, dy)
+            self.add_grad(W, ops.linear_bwd_weight(dy, x))
+            if b is not None:
+                self.add_grad(b, ops.colsum(dy))
+            self.add_grad(x, ops.linear_bwd_data(dy, W))
+        self._push(bwd)
+        return y
+
+    def linear_cat(self, parts: Sequence[Tensor], W4: Tensor, b: Tensor) -> Tensor:
+        """1x1 convolution over the channel-concatenation of `parts` ([P,Ci] each) without
+        materialising the cat (tsrn.py:902 + 1075): y = sum_i parts_i @ W[:, off_i:off_i+Ci]^T + b."""
+        W = W4.view(W4.shape[0], -1)
+        y = None
+        off = 0
+        for t in parts:
+            ci = t.shape[1]
+            y = ops.linear_fwd(t, W[:, off:off + ci], b if off == 0 else None, out=y, accumulate=off > 0)
+            off += ci
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is None:
+                return
+            dW = ops.zeros(W.shape[0], W.shape[1], like=dy)
+            o = 0
+            for t in parts:
+                ci = t.shape[1]
+                ops.linear_bwd_weight(dy, t, out=dW[:, o:o + ci])
+                self.add_grad(t, ops.linear_bwd_data(dy, W[:, o:o + ci]))
+                o += ci
+            self.add_grad(W4, dW.view_as(W4))
+            self.add_grad(b, ops.colsum(dy))
+        self._push(bwd)
+        return y
+
+    def conv(self, x4: Tensor, w: Tensor, b: Optional[Tensor], pad: int, need_dx: bool = True) -> Tensor:
+        y = ops.conv2d_fwd(x4, w, b, pad)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is None:
+                return
+            dx, dw, db = ops.conv2d_bwd(x4, w, dy, pad, need_dx=need_dx, has_bias=b is not None)
+            self.add_grad(w, dw)
+            if b is not None:
+                self.add_grad(b, db)
+            if need_dx:
+                self.add_grad(x4, dx)
+        self._push(bwd)
+        return y
+
+    # ------------------------------------------------------------------ normalisation
+    def batchnorm(self, x: Tensor, bn: torch.nn.Module, act: int, training: bool) -> Tensor:
+        """BatchNorm over all leading dims of a channels-last tensor, fused activation."""
+        C = x.shape[-1]
+        x2 = x.view(-1, C)
+        use_batch = training or bn.running_mean is None
+        if use_batch:
+            mean, invstd = ops.bn_stats(x2, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                                        bn.running_mean if training else None, bn.running_var if training else None)
+            if training and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+        else:
+            mean, invstd = ops.bn_eval_stats(bn.running_mean, bn.running_var, bn.eps)
+        gamma, beta = bn.weight, bn.bias
+        y = ops.bn_apply(x2, mean, invstd, gamma, beta, act).view(x.shape)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is None:
+                return
+            dx, dg, db = ops.bn_bwd(x2, dy.view(-1, C), mean, invstd, gamma, beta, act, use_batch)
+            self.add_grad(gamma, dg)
+            self.add_grad(beta, db)
+            self.add_grad(x, dx.view(x.shape))
+        self._push(bwd)
+        return y
+
+    def add_layernorm(self, x: Tensor, r: Optional[Tensor], ln: torch.nn.Module) -> Tensor:
+        """LN(x + r) over 64 channels."""
+        y, S, st = ops.layernorm_fwd(x, r, ln.weight, ln.bias, save=self.record)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is None:
+                return
+            dS, dg, db = ops.layernorm_bwd(dy, S, st, ln.weight)
+            self.add_grad(ln.weight, dg)
+            self.add_grad(ln.bias, db)
+            self.add_grad(x, dS)
+            if r is not None:
+                self.add_grad(r, dS)
+        self._push(bwd)
+        return y
+
+    # ------------------------------------------------------------------ element-wise
+    def view(self, x: Tensor, *shape) -> Tensor:
+        """Reshape with gradient pass-through (grads are keyed by tensor identity)."""
+        y = x.view(*shape)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is not None:
+                self.add_grad(x, dy.view(x.shape))
+        self._push(bwd)
+        return y
+
+    def add(self, a: Tensor, b: Tensor) -> Tensor:
+        y = ops.add(a, b)
+
+        def bwd():
+            dy = self.grad(y)
+            self.add_grad(a, dy)
+            self.add_grad(b, dy)
+        self._push(bwd)
+        return y
+
+    def scale(self, a: Tensor, alpha: float) -> Tensor:
+        y = ops.axpby(a, None, alpha, 0.0)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is not None:
+                self.add_grad(a, ops.axpby(dy, None, alpha, 0.0))
+        self._push(bwd)
+        return y
+
+    def mean2(self, a: Tensor, b: Tensor) -> Tensor:
+        y = ops.axpby(a, b, 0.5, 0.5)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is not None:
+                h = ops.axpby(dy, None, 0.5, 0.0)
+                self.add_grad(a, h)
+                self.add_grad(b, h)
+        self._push(bwd)
+        return y
+
+    def prelu(self, x: Tensor, w: Tensor) -> Tensor:
+        y = ops.prelu_fwd(x, w)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is None:
+                return
+            dx, dw = ops.prelu_bwd(x, w, dy)
+            self.add_grad(w, dw)
+            self.add_grad(x, dx)
+        self._push(bwd)
+        return y
+
+    def dropout(self, x: Tensor, p: float, rng: Optional[Tensor], site: int) -> Tensor:
+        if p <= 0.0 or rng is None:
+            return x
+        y = ops.dropout(x, p, rng, site)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is not None:
+                self.add_grad(x, ops.dropout(dy, p, rng, site))
+        self._push(bwd)
+        return y
+
+    def pixshuf_mish(self, x4: Tensor) -> Tensor:
+        y = ops.pixshuf2_mish_fwd(x4)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is not None:
+                self.add_grad(x4, ops.pixshuf2_mish_bwd(x4, dy))
+        self._push(bwd)
+        return y
+
+    def maxpool(self, x4: Tensor, kh: int, kw: int) -> Tensor:
+        y = ops.maxpool_fwd(x4, kh, kw)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is not None:
+                self.add_grad(x4, ops.maxpool_bwd(x4, dy, kh, kw))
+        self._push(bwd)
+        return y
+
+    def to_nchw(self, x4: Tensor, c: int, tanh: bool = False) -> Tensor:
+        """NHWC (padded channels) -> NCHW (first c channels), optional tanh."""
+        y = ops.nhwc_to_nchw(x4, c, do_tanh=tanh)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is not None:
+                self.add_grad(x4, ops.tanh_bwd_to_nhwc(dy, y if tanh else None, x4.shape[-1]))
+        self._push(bwd)
+        return y
+
+    def to_nhwc(self, x: Tensor, cp: int) -> Tensor:
+        y = ops.nchw_to_nhwc(x, cp)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is not None:
+                self.add_grad(x, ops.nhwc_to_nchw(dy, x.shape[1]))
+        self._push(bwd)
+        return y
+
+    # ------------------------------------------------------------------ recurrent / attention composites
+    def bigru32(self, c: Tensor, gru: torch.nn.GRU, nseq: int, T: int, s_inner: int, outer: int, inner: int,
+                tstride: int) -> Tensor:
+        """nn.GRU(64, 32, bidirectional) over strided sequences of the row tensor c [P,64]."""
+        P = c.shape[0]
+        w_ih = (gru.weight_ih_l0, gru.weight_ih_l0_reverse)
+        w_hh = (gru.weight_hh_l0, gru.weight_hh_l0_reverse)
+        b_ih = (gru.bias_ih_l0, gru.bias_ih_l0_reverse)
+        b_hh = (gru.bias_hh_l0, gru.bias_hh_l0_reverse)
+        gi = ops.empty(P, 192, like=c)
+        whh = ops.empty(2, 96, 32, like=c)
+        bhh = ops.empty(2, 96, like=c)
+        for d in range(2):
+            ops.linear_fwd(c, w_ih[d], b_ih[d], out=gi[:, d * 96:(d + 1) * 96])
+            ops.memcpy(whh[d], w_hh[d])
+            ops.memcpy(bhh[d], b_hh[d])
+        out, gates = ops.gru32_scan_fwd(gi, whh, bhh, nseq, T, s_inner, outer, inner, tstride, save=self.record)
+        del gi
+
+        def bwd():
+            dout = self.grad(out)
+            if dout is None:
+                return
+            dgi, dgh = ops.gru32_scan_bwd(dout, gates, whh, nseq, T, s_inner, outer, inner, tstride)
+            dc = None
+            for d in range(2):
+                gi_d = dgi[:, d * 96:(d + 1) * 96]
+                gh_d = dgh[:, d * 96:(d + 1) * 96]
+                hprev = gates[:, d * 160 + 128:d * 160 + 160]
+                self.add_grad(w_hh[d], ops.linear_bwd_weight(gh_d, hprev))
+                self.add_grad(b_hh[d], ops.colsum(gh_d))
+                self.add_grad(w_ih[d], ops.linear_bwd_weight(gi_d, c))
+                self.add_grad(b_ih[d], ops.colsum(gi_d))
+                dc = ops.linear_bwd_data(gi_d, w_ih[d], out=dc, accumulate=d > 0)
+            self.add_grad(c, dc)
+        self._push(bwd)
+        return out
+
+    def mha(self, q_in: Tensor, k_in: Tensor, v_in: Tensor, attn: torch.nn.MultiheadAttention, N: int, Lq: int,
+            Lk: int, need_weights: bool, pdrop: float, rng: Optional[Tensor], site: int):
+        """nn.MultiheadAttention(64, 4) on token-major [N*L, 64] inputs -> (out [N*Lq,64], weights)."""
+        Win, bin_ = attn.in_proj_weight, attn.in_proj_bias
+        Wo, bo = attn.out_proj.weight, attn.out_proj.bias
+        q = ops.linear_fwd(q_in, Win[0:64], bin_[0:64])
+        k = ops.linear_fwd(k_in, Win[64:128], bin_[64:128])
+        v = ops.linear_fwd(v_in, Win[128:192], bin_[128:192])
+        if pdrop <= 0.0 or rng is None:
+            pdrop, rng_ = 0.0, None
+        else:
+            rng_ = rng
+        a, aw = ops.mha_fwd(q, k, v, N, Lq, Lk, need_weights, pdrop, rng_, site)
+        y = ops.linear_fwd(a, Wo, bo)
+
+        def bwd():
+            dy = self.grad(y)
+            if dy is None:
+                return
+            self.add_grad(Wo, ops.linear_bwd_weight(dy, a))
+            self.add_grad(bo, ops.colsum(dy))
+            da = ops.linear_bwd_data(dy, Wo)
+            dq, dk, dv = ops.mha_bwd(q, k, v, da, N, Lq, Lk, pdrop, rng_, site)
+            dWin = ops.zeros(192, 64, like=dy)
+            dbin = ops.empty(192, like=dy)
+            for i, (g, src) in enumerate(((dq, q_in), (dk, k_in), (dv, v_in))):
+                ops.linear_bwd_weight(g, src, out=dWin[i * 64:(i + 1) * 64])
+                ops.colsum(g, out=dbin[i * 64:(i + 1) * 64])
+                self.add_grad(src, ops.linear_bwd_data(g, Win[i * 64:(i + 1) * 64]))
+            self.add_grad(Win, dWin)
+            self.add_grad(bin_, dbin)
+        self._push(bwd)
+        return y, aw

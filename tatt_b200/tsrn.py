@@ -1,0 +1,395 @@
+"""Drop-in `TSRN` / `TSRN_TL_TRANS` (the reference's `model/tsrn.py` surface for --arch=tsrn / --arch=tatt).
+
+Same constructor signatures, same `forward` signatures / return structures, same `state_dict`
+layout (names, shapes, buffers, the dead Q3 tensors) and -- because the same torch.nn leaf modules are
+created in the same order -- bit-identical fresh initialisation under the same seed
+(reference: model/tsrn.py:88-150, 155-224, 576-692, 850-910, 1040-1084; model/transformer_v2.py:22-42,
+154-196, 248-259, 346-353, 448-466, 773-800; model/stn_head.py:25-90; model/tps_spatial_transformer.py:22-95).
+
+The torch.nn leaves are PARAMETER CONTAINERS only: no nn.Module.forward of theirs is ever called.
+All arithmetic runs in the hand-written sm_100a kernels behind the C-ABI (include/tatt_b200.h) via
+tatt_b200.stages.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import copy
+import itertools
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import stages
+
+__all__ = ["TSRN", "TSRN_TL_TRANS", "TPInterpreter", "InfoTransformer", "RecurrentResidualBlock",
+           "RecurrentResidualBlockTL", "GruBlock", "UpsampleBLock", "mish", "STNHead", "TPSSpatialTransformer",
+           "PositionalEncoding"]
+
+
+def _no_forward(self, *a, **k):
+    raise RuntimeError("%s is a parameter container in tatt_b200; its math runs inside the fused CUDA stages"
+                       % type(self).__name__)
+
+
+def _require_cuda(x: torch.Tensor) -> None:
+    if not x.is_cuda:
+        raise RuntimeError("tatt_b200 runs on sm_100a only: got a %s tensor (no CPU fallback exists)" % x.device)
+
+
+# ------------------------------------------------------------------------------- leaf containers
+class mish(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.activated = True
+    forward = _no_forward
+
+
+class GruBlock(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        assert out_channels % 2 == 0
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=1, padding=0)
+        self.gru = nn.GRU(out_channels, out_channels // 2, bidirectional=True, batch_first=True)
+    forward = _no_forward
+
+
+class _SRBBase(nn.Module):
+    def _make(self, channels, gru1_in):
+        self.conv1 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
+        self.bn1 = nn.BatchNorm2d(channels)
+        self.gru1 = GruBlock(gru1_in, channels)
+        self.prelu = mish()
+        self.conv2 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
+        self.bn2 = nn.BatchNorm2d(channels)
+        self.gru2 = GruBlock(channels, channels)
+
+
+class RecurrentResidualBlock(_SRBBase):
+    def __init__(self, channels):
+        super().__init__()
+        self._make(channels, channels)
+
+    def forward(self, x):
+        return stages.srb_stage(self, x, None, self.training)
+
+
+class RecurrentResidualBlockTL(_SRBBase):
+    def __init__(self, channels, text_channels):
+        super().__init__()
+        self._make(channels, channels + text_channels)
+
+    def forward(self, x, text_emb):
+        return stages.srb_stage(self, x, text_emb, self.training)
+
+
+class UpsampleBLock(nn.Module):
+    def __init__(self, in_channels, up_scale):
+        super().__init__()
+        if up_scale != 2:
+            raise NotImplementedError("tatt_b200 fuses PixelShuffle(2) only")
+        self.conv = nn.Conv2d(in_channels, in_channels * up_scale ** 2, kernel_size=3, padding=1)
+        self.pixel_shuffle = nn.PixelShuffle(up_scale)
+        self.prelu = mish()
+    forward = _no_forward
+
+
+class PositionalEncoding(nn.Module):
+    def __init__(self, d_model, dropout, max_len=5000):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        pos = torch.arange(0, max_len).unsqueeze(1).float()
+        div = torch.exp(torch.arange(0, d_model, 2).float() * -(math.log(10000.0) / d_model))
+        table = torch.zeros(max_len, d_model)
+        table[:, 0::2] = torch.sin(pos * div)
+        table[:, 1::2] = torch.cos(pos * div)
+        self.register_buffer("pe", table.unsqueeze(0))
+    forward = _no_forward
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, dim_ff, dropout):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_ff)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_ff, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.normalize_before = False
+    forward = _no_forward
+
+
+class _DecoderLayerTP(nn.Module):
+    """Holds self_attn / norm1 like the reference even though its forward never uses them (Q3)."""
+
+    def __init__(self, d_model, nhead, dim_ff, dropout):
+        super().__init__()
+        self.d_model_self = 1024
+        self.d_model = d_model
+        self.height, self.width = 16, 64
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.multihead_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_ff)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_ff, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.normalize_before = False
+    forward = _no_forward
+
+
+class _LayerStack(nn.Module):
+    def __init__(self, layer, num_layers, norm=None, return_intermediate=False):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = norm
+        self.return_intermediate = return_intermediate
+    forward = _no_forward
+
+
+class InfoTransformer(nn.Module):
+    def __init__(self, d_model=1024, nhead=8, num_encoder_layers=3, num_decoder_layers=3, dim_feedforward=2048,
+                 dropout=0.1, activation="relu", normalize_before=False, return_intermediate_dec=False,
+                 feat_height=16, feat_width=64):
+        super().__init__()
+        if normalize_before or activation != "relu" or num_encoder_layers != 1 or num_decoder_layers != 2:
+            raise NotImplementedError("tatt_b200 implements the configuration TPInterpreter instantiates")
+        self.encoder = _LayerStack(_EncoderLayer(d_model, nhead, dim_feedforward, dropout), num_encoder_layers, None)
+        self.decoder = _LayerStack(_DecoderLayerTP(d_model, nhead, dim_feedforward, dropout), num_decoder_layers,
+                                   nn.LayerNorm(d_model), return_intermediate=return_intermediate_dec)
+        self.gru_encoding = nn.GRU(d_model * feat_height, d_model * feat_height // 2, bidirectional=True,
+                                   batch_first=True)
+        for p in self.parameters():      # _reset_parameters: xavier on every matrix, GRU included
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self.d_model, self.nhead = d_model, nhead
+        self.feat_size = (feat_height, feat_width)
+    forward = _no_forward
+
+
+class TPInterpreter(nn.Module):
+    def __init__(self, t_emb, out_text_channels, output_size=(16, 64), feature_in=64, t_encoder_num=1,
+                 t_decoder_num=2):
+        super().__init__()
+        d_model = out_text_channels
+        if d_model != 64:
+            raise NotImplementedError("tatt_b200 attention/LayerNorm kernels are specialised for d_model=64")
+        self.fc_in = nn.Linear(t_emb, d_model)
+        self.fc_feature_in = nn.Linear(feature_in, d_model)      # never used by the reference forward (Q3)
+        self.activation = nn.PReLU()
+        self.transformer = InfoTransformer(d_model=d_model, dropout=0.1, nhead=4, dim_feedforward=d_model,
+                                           num_encoder_layers=t_encoder_num, num_decoder_layers=t_decoder_num,
+                                           normalize_before=False, return_intermediate_dec=True,
+                                           feat_height=output_size[0], feat_width=output_size[1])
+        self.pe = PositionalEncoding(d_model=d_model, dropout=0.1, max_len=5000)
+        self.output_size = output_size
+        self.seq_len = output_size[1] * output_size[0]
+        self.init_factor = nn.Embedding(self.seq_len, d_model)
+        self.masking = torch.ones(output_size)
+        self._qpos_cache = None
+
+    def query_pos(self, batch, H, W):
+        """Recurrent positional encoding [batch, H*W, 64].  It depends on (weights, batch) only, so
+        without autograd it is cached until a weight changes."""
+        gru = self.transformer.gru_encoding
+        ps = [self.init_factor.weight] + list(gru.parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in ps):
+            return stages.rpe_stage(self.init_factor, gru, batch, H, W)
+        key = (batch, H, W, ps[0].device) + tuple((p.data_ptr(), p._version) for p in ps)
+        if self._qpos_cache is None or self._qpos_cache[0] != key:
+            with torch.no_grad():
+                self._qpos_cache = (key, stages.rpe_stage(self.init_factor, gru, batch, H, W))
+        return self._qpos_cache[1]
+
+    def forward(self, image_feature, tp_input):
+        N, C, H, W = image_feature.shape
+        qpos = self.query_pos(tp_input.shape[0], H, W)
+        return stages.tp_stage(self, image_feature, tp_input, qpos, self.training)
+
+
+# ------------------------------------------------------------------------------- STN / TPS containers
+def _tps_basis(points, ctrl):
+    d = points.view(-1, 1, 2) - ctrl.view(1, -1, 2)
+    d2 = d * d
+    r2 = d2[:, :, 0] + d2[:, :, 1]
+    u = 0.5 * r2 * torch.log(r2)
+    u.masked_fill_(u != u, 0)
+    return u
+
+
+def _edge_control_points(n, margins):
+    mx, my = margins
+    k = n // 2
+    xs = np.linspace(mx, 1.0 - mx, k)
+    top = np.stack([xs, np.ones(k) * my], axis=1)
+    bot = np.stack([xs, np.ones(k) * (1.0 - my)], axis=1)
+    return torch.Tensor(np.concatenate([top, bot], axis=0))
+
+
+class TPSSpatialTransformer(nn.Module):
+    def __init__(self, output_image_size=None, num_control_points=None, margins=None):
+        super().__init__()
+        self.output_image_size = output_image_size
+        self.num_control_points = num_control_points
+        self.margins = margins
+        self.target_height, self.target_width = output_image_size
+        ctrl = _edge_control_points(num_control_points, margins)
+        n = num_control_points
+        fwd = torch.zeros(n + 3, n + 3)
+        fwd[:n, :n].copy_(_tps_basis(ctrl, ctrl))
+        fwd[:n, -3].fill_(1)
+        fwd[-3, :n].fill_(1)
+        fwd[:n, -2:].copy_(ctrl)
+        fwd[-2:, :n].copy_(ctrl.transpose(0, 1))
+        inv = torch.inverse(fwd)
+        hw = self.target_height * self.target_width
+        yx = torch.Tensor(list(itertools.product(range(self.target_height), range(self.target_width))))
+        Y, X = yx.split(1, dim=1)
+        xy = torch.cat([X / (self.target_width - 1), Y / (self.target_height - 1)], dim=1)
+        rep = torch.cat([_tps_basis(xy, ctrl), torch.ones(hw, 1), xy], dim=1)
+        self.register_buffer("inverse_kernel", inv)
+        self.register_buffer("padding_matrix", torch.zeros(3, 2))
+        self.register_buffer("target_coordinate_repr", rep)
+        self.register_buffer("target_control_points", ctrl)
+    forward = _no_forward
+
+
+def _conv3x3_block(cin, cout):
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(cout),
+                         nn.ReLU(inplace=True))
+
+
+class STNHead(nn.Module):
+    def __init__(self, in_planes, num_ctrlpoints, activation="none", input_size=(16, 64)):
+        super().__init__()
+        if activation != "none":
+            raise NotImplementedError("tatt_b200 implements the activation='none' head TSRN instantiates")
+        self.in_planes, self.num_ctrlpoints, self.activation = in_planes, num_ctrlpoints, activation
+        chans = [(in_planes, 32), (32, 64), (64, 128), (128, 256), (256, 256), (256, 256)]
+        layers = []
+        for i, (a, b) in enumerate(chans):
+            layers.append(_conv3x3_block(a, b))
+            if i < 4:
+                layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+            elif i == 4:
+                layers.append(nn.MaxPool2d(kernel_size=(1, 2), stride=(1, 2)))
+        self.stn_convnet = nn.Sequential(*layers)
+        self.stn_fc1 = nn.Sequential(nn.Linear(512, 512), nn.BatchNorm1d(512), nn.ReLU(inplace=True))
+        self.stn_fc2 = nn.Linear(512, num_ctrlpoints * 2)
+        for seq in (self.stn_convnet, self.stn_fc1):
+            for m in seq.modules():
+                if isinstance(m, nn.Conv2d):
+                    m.weight.data.normal_(0, math.sqrt(2.0 / (m.kernel_size[0] * m.kernel_size[1] * m.out_channels)))
+                    m.bias.data.zero_()
+                elif isinstance(m, nn.BatchNorm2d):
+                    m.weight.data.fill_(1)
+                    m.bias.data.zero_()
+                elif isinstance(m, nn.Linear):
+                    m.weight.data.normal_(0, 0.001)
+                    m.bias.data.zero_()
+        k = num_ctrlpoints // 2
+        xs = np.linspace(0.01, 0.99, k)
+        pts = np.concatenate([np.stack([xs, np.ones(k) * 0.01], 1), np.stack([xs, np.ones(k) * 0.99], 1)], 0)
+        self.stn_fc2.weight.data.zero_()
+        self.stn_fc2.bias.data = torch.Tensor(pts.astype(np.float32)).view(-1)
+    forward = _no_forward
+
+
+# ------------------------------------------------------------------------------- the two models
+class _TSRNBase(nn.Module):
+    def _build_trunk(self, scale_factor, width, height, STN, srb_nums, mask, hidden_units, make_srb):
+        in_planes = 4 if mask else 3
+        assert math.log(scale_factor, 2) % 1 == 0
+        n_up = int(math.log(scale_factor, 2))
+        ch = 2 * hidden_units
+        self.block1 = nn.Sequential(nn.Conv2d(in_planes, ch, kernel_size=9, padding=4), nn.PReLU())
+        self.srb_nums = srb_nums
+        for i in range(srb_nums):
+            setattr(self, "block%d" % (i + 2), make_srb(ch))
+        return in_planes, n_up, ch
+
+    def _build_tail(self, in_planes, n_up, ch, scale_factor, width, height, STN, srb_nums, pass_size):
+        setattr(self, "block%d" % (srb_nums + 2),
+                nn.Sequential(nn.Conv2d(ch, ch, kernel_size=3, padding=1), nn.BatchNorm2d(ch)))
+        tail = [UpsampleBLock(ch, 2) for _ in range(n_up)]
+        tail.append(nn.Conv2d(ch, in_planes, kernel_size=9, padding=4))
+        setattr(self, "block%d" % (srb_nums + 3), nn.Sequential(*tail))
+        self.tps_inputsize = [height // scale_factor, width // scale_factor]
+        self.stn = STN
+        if self.stn:
+            self.tps = TPSSpatialTransformer(output_image_size=tuple(self.tps_inputsize), num_control_points=20,
+                                             margins=(0.05, 0.05))
+            kw = {"input_size": self.tps_inputsize} if pass_size else {}
+            self.stn_head = STNHead(in_planes=in_planes, num_ctrlpoints=20, activation="none", **kw)
+        self._in_planes = in_planes
+
+    def _stem(self, x):
+        _require_cuda(x)
+        if x.dim() != 4 or x.shape[1] != self._in_planes:
+            raise RuntimeError("expected input [N, %d, H, W], got %s" % (self._in_planes, tuple(x.shape)))
+        if self.stn and self.training:
+            xw = stages.stn_tps_stage(self.stn_head, self.tps, x, True)
+            return stages.stem_stage(self.block1, xw, True)
+        return stages.stem_stage(self.block1, x, False)
+
+
+class TSRN(_TSRNBase):
+    def __init__(self, scale_factor=2, width=128, height=32, STN=False, srb_nums=5, mask=True, hidden_units=32):
+        super().__init__()
+        ip, n_up, ch = self._build_trunk(scale_factor, width, height, STN, srb_nums, mask, hidden_units,
+                                         lambda c: RecurrentResidualBlock(c))
+        self._build_tail(ip, n_up, ch, scale_factor, width, height, STN, srb_nums, pass_size=False)
+
+    def forward(self, x):
+        block = {"1": self._stem(x)}
+        k = self.srb_nums + 2
+        for i in range(2, k):
+            block[str(i)] = stages.srb_stage(getattr(self, "block%d" % i), block[str(i - 1)], None, self.training)
+        block[str(k)] = stages.conv_bn_stage(getattr(self, "block%d" % k), block[str(k - 1)], self.training)
+        out, pre = stages.tail_stage(getattr(self, "block%d" % (k + 1)), block["1"], block[str(k)], self._in_planes)
+        block[str(k + 1)] = pre
+        self.block = block
+        return out
+
+
+class TSRN_TL_TRANS(_TSRNBase):
+    def __init__(self, scale_factor=2, width=128, height=32, STN=False, srb_nums=5, mask=True, hidden_units=32,
+                 word_vec_d=300, text_emb=37, out_text_channels=64, feature_rotate=False, rotate_train=3.):
+        super().__init__()
+        ip, n_up, ch = self._build_trunk(scale_factor, width, height, STN, srb_nums, mask, hidden_units,
+                                         lambda c: RecurrentResidualBlockTL(c, out_text_channels))
+        self.infoGen = TPInterpreter(text_emb, out_text_channels,
+                                     output_size=(height // scale_factor, width // scale_factor))
+        self.feature_rotate = feature_rotate
+        self.rotate_train = rotate_train
+        self._build_tail(ip, n_up, ch, scale_factor, width, height, STN, srb_nums, pass_size=True)
+        self.block_range = [k for k in range(2, self.srb_nums + 2)]
+        self._text_emb = text_emb
+
+    def forward(self, x, text_emb=None, text_emb_gt=None, feature_arcs=None, rand_offs=None):
+        block = {"1": self._stem(x)}
+        if text_emb is None:
+            text_emb = torch.zeros(1, self._text_emb, 1, 26, device=x.device)
+        tp_map, pr_weights = self.infoGen(block["1"], text_emb)
+        k = self.srb_nums + 2
+        for i in range(2, k + 1):
+            blk = getattr(self, "block%d" % i)
+            if i in self.block_range:
+                block[str(i)] = stages.srb_stage(blk, block[str(i - 1)], tp_map, self.training)
+            else:
+                block[str(i)] = stages.conv_bn_stage(blk, block[str(i - 1)], self.training)
+        out, pre = stages.tail_stage(getattr(self, "block%d" % (k + 1)), block["1"], block[str(k)], self._in_planes)
+        block[str(k + 1)] = pre
+        self.block = block
+        if self.training:
+            return out, {"pr_weights": pr_weights, "pr_weights_gt": None, "spatial_t_emb": tp_map,
+                         "spatial_t_emb_gt": None, "in_feat": block["1"], "trans_feat": tp_map}
+        return out, pr_weights

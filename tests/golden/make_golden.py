@@ -1,0 +1,55 @@
+"""Generate tests/golden/*.pt from the LIVE reference (/root/reference, imported unmodified through
+oracle/ref_harness.py).  Run in the build container only:  python tests/golden/make_golden.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import golden_util as gu  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+from oracle import tatt_oracle as orc  # noqa: E402
+
+
+def main():
+    ref = rh.load()
+    for name, (cls, kw, N, training) in gu.CASES.items():
+        torch.manual_seed(gu.SEED)
+        net = getattr(ref, cls)(**kw)
+        rh.zero_dropout(net)
+        rh.perturb_(net)
+        net.train(training)
+        h, w = kw["height"] // 2, kw["width"] // 2
+        x, tp = orc.synthetic_inputs(N, h, w, seed=gu.SEED, with_mask=kw.get("mask", True))
+        fx = {"case": name, "torch": torch.__version__}
+        if cls == "TSRN":
+            out = net(x)
+            aux = None
+        else:
+            out, aux = net(x, tp)
+        fx["out"] = gu.summarize(out)
+        if aux is not None:
+            pw = aux["pr_weights"] if training else aux
+            fx["pr_weights"] = gu.summarize(pw)
+            if training:
+                fx["tp_map"] = gu.summarize(aux["spatial_t_emb"])
+        for k in ("1", "4", str(kw.get("srb_nums", 5) + 2)):
+            fx["block" + k] = gu.summarize(net.block[k], nsamp=256)
+        if training:
+            # loss exercising every output element with non-uniform weights
+            gen = torch.Generator().manual_seed(99)
+            wgt = torch.randn(out.shape, generator=gen)
+            (out * wgt).sum().backward()
+            fx["grads"] = {n: (None if p.grad is None else gu.summarize(p.grad, nsamp=8))
+                           for n, p in net.named_parameters()}
+            fx["buffers"] = {n: gu.summarize(b.float(), nsamp=4) for n, b in net.named_buffers()
+                             if "running" in n or "num_batches" in n}
+        path = os.path.join(gu.GOLDEN_DIR, name + ".pt")
+        torch.save(fx, path)
+        print(name, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

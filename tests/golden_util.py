@@ -1,0 +1,47 @@
+"""Shared helpers for the golden fixtures (tests/golden/*.pt).
+
+A fixture stores, for one (model class, geometry, batch, mode) case generated from the LIVE reference
+(tests/golden/make_golden.py): strided samples + float64 checksums of the outputs, and per-parameter
+gradient summaries (sum, L2 norm, a few sampled elements).  Weights are not stored: they are the
+seed-1234 fresh init (bit-identical between the reference and tatt_b200, pinned by
+tests/test_dropin_surface.py) followed by oracle.ref_harness.perturb_ (seeded), inputs are
+oracle.tatt_oracle.synthetic_inputs (seeded)."""
+import os
+
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CASES = {
+    # name: (class, ctor kwargs, N, training)
+    "tatt_g16_stn_train_n3": ("TSRN_TL_TRANS", dict(scale_factor=2, width=128, height=32, STN=True, mask=True), 3, True),
+    "tatt_g16_eval_n2": ("TSRN_TL_TRANS", dict(scale_factor=2, width=128, height=32, STN=True, mask=True), 2, False),
+    "tatt_g32_train_n2": ("TSRN_TL_TRANS", dict(scale_factor=2, width=256, height=64, STN=False, mask=True), 2, True),
+    "tatt_tiny_rgb_train_n2": ("TSRN_TL_TRANS", dict(scale_factor=2, width=32, height=16, STN=False, mask=False), 2, True),
+    "tsrn_g16_stn_train_n3": ("TSRN", dict(scale_factor=2, width=128, height=32, STN=True, mask=True), 3, True),
+}
+SEED = 1234
+
+
+def summarize(t: torch.Tensor, nsamp: int = 1024):
+    t = t.detach().double().cpu().reshape(-1)
+    d = {"sum": t.sum().item(), "l2": t.norm().item(), "n": t.numel()}
+    nsamp = min(nsamp, t.numel())
+    idx = torch.linspace(0, t.numel() - 1, nsamp).long()
+    d["idx"], d["val"] = idx.int(), t[idx].float()
+    return d
+
+
+def check_summary(name: str, t: torch.Tensor, ref: dict, tol: float):
+    t = t.detach().double().cpu().reshape(-1)
+    assert t.numel() == ref["n"], (name, t.numel(), ref["n"])
+    scale = max(ref["l2"] / max(ref["n"], 1) ** 0.5, 1e-12)           # rms of the reference tensor
+    got, want = t[ref["idx"].long()].float(), ref["val"]
+    err = (got - want).abs().max().item()
+    assert err <= tol * max(want.abs().max().item(), scale), "%s: sample err %.3e (scale %.3e)" % (name, err, scale)
+    l2 = t.norm().item()
+    assert abs(l2 - ref["l2"]) <= tol * max(ref["l2"], 1e-12), "%s: l2 %.6e vs %.6e" % (name, l2, ref["l2"])
+
+
+def load(name: str) -> dict:
+    return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)

@@ -1,0 +1,168 @@
+"""End-to-end parity of the drop-in modules (CUDA, through the C-ABI) against the oracle restatement and
+the committed reference fixtures.  Stated tolerances (fp32): outputs / intermediates <= 1e-3 relative to
+the tensor's max-abs (north_star bound); parameter gradients <= 2e-3 relative to the gradient's max-abs
+(split-K / atomic accumulation order differs from the CPU's)."""
+import pytest
+import torch
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def relerr(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+def make(case, zero_drop=True):
+    import tatt_b200
+    from oracle import ref_harness as rh
+    from oracle import tatt_oracle as orc
+    cls, kw, N, training = gu.CASES[case]
+    torch.manual_seed(gu.SEED)
+    net = getattr(tatt_b200, cls)(**kw)
+    if zero_drop:
+        rh.zero_dropout(net)
+    rh.perturb_(net)
+    net.train(training)
+    sd = orc.clone_sd(net.state_dict(), requires_grad=training)
+    x, tp = orc.synthetic_inputs(N, kw["height"] // 2, kw["width"] // 2, seed=gu.SEED, with_mask=kw.get("mask", True))
+    return net.to(DEV), sd, x, tp, cls, kw, N, training
+
+
+def run_oracle(cls, kw, sd, x, tp, training):
+    from oracle import tatt_oracle as orc
+    if cls == "TSRN":
+        out, block = orc.tsrn_forward(sd, x, training=training, stn=kw["STN"])
+        return out, None, block
+    return orc.tsrn_tl_trans_forward(sd, x, tp, training=training, stn=kw["STN"], dropout_p=0.0)
+
+
+@pytest.mark.parametrize("case", list(gu.CASES))
+def test_forward_backward_vs_oracle_and_golden(case):
+    net, sd, x, tp, cls, kw, N, training = make(case)
+    fx = gu.load(case)
+    xo = x.to(DEV)
+    if cls == "TSRN":
+        out, aux = net(xo), None
+    else:
+        out, aux = net(xo, tp.to(DEV))
+    o_out, o_aux, o_block = run_oracle(cls, kw, sd, x, tp, training)
+    assert out.shape == o_out.shape and out.dtype == torch.float32
+    assert relerr(out, o_out) <= 1e-3, "output vs oracle: %.3e" % relerr(out, o_out)
+    gu.check_summary("out", out, fx["out"], 1e-3)
+    for k in o_block:
+        e = relerr(net.block[k], o_block[k])
+        assert e <= 1e-3, "block %s vs oracle: %.3e" % (k, e)
+        if "block" + k in fx:
+            gu.check_summary("block" + k, net.block[k], fx["block" + k], 1e-3)
+    if aux is not None:
+        pw = aux["pr_weights"] if training else aux
+        opw = o_aux["pr_weights"] if training else o_aux
+        assert relerr(pw, opw) <= 1e-3
+        assert (pw.sum(-1) - 1).abs().max().item() < 1e-4          # rows of the averaged attention sum to 1
+        gu.check_summary("pr_weights", pw, fx["pr_weights"], 1e-3)
+        if training:
+            assert set(aux.keys()) == {"pr_weights", "pr_weights_gt", "spatial_t_emb", "spatial_t_emb_gt",
+                                       "in_feat", "trans_feat"}
+            assert relerr(aux["spatial_t_emb"], o_aux["spatial_t_emb"]) <= 1e-3
+            gu.check_summary("tp_map", aux["spatial_t_emb"], fx["tp_map"], 1e-3)
+    if not training:
+        return
+    gen = torch.Generator().manual_seed(99)
+    wgt = torch.randn(out.shape, generator=gen)
+    (out * wgt.to(DEV)).sum().backward()
+    (o_out * wgt).sum().backward()
+    worst = ("", 0.0)
+    for n, p in net.named_parameters():
+        og = sd[n].grad
+        ref = fx["grads"][n]
+        if ref is None:                      # Q3 dead parameters never receive a gradient
+            assert p.grad is None, n
+            assert og is None or og.abs().max().item() == 0
+            continue
+        assert p.grad is not None, n
+        if og.abs().max().item() == 0:
+            assert p.grad.abs().max().item() <= 1e-6, n
+            continue
+        e = relerr(p.grad, og)
+        if e > worst[1]:
+            worst = (n, e)
+        assert e <= 2e-3, "grad %s vs oracle: %.3e" % (n, e)
+        gu.check_summary("grad " + n, p.grad, ref, 2e-3)
+    # BatchNorm running statistics were updated exactly like torch does
+    for n, b in net.named_buffers():
+        if "running" in n or "num_batches" in n:
+            assert relerr(b.float(), sd[n].float()) <= 1e-4, n
+            gu.check_summary("buffer " + n, b.float(), fx["buffers"][n], 1e-4)
+    print("worst grad", worst)
+
+
+def test_eval_repeatable_and_qpos_cache():
+    net, sd, x, tp, cls, kw, N, training = make("tatt_g16_eval_n2")
+    with torch.no_grad():
+        a, wa = net(x.to(DEV), tp.to(DEV))
+        cache = net.infoGen._qpos_cache
+        b, wb = net(x.to(DEV), tp.to(DEV))
+    assert torch.equal(a, b) and torch.equal(wa, wb)
+    assert net.infoGen._qpos_cache is cache                      # RPE reused: weights unchanged
+    with torch.no_grad():
+        net.infoGen.init_factor.weight.mul_(1.5)
+        c, _ = net(x.to(DEV), tp.to(DEV))
+    assert net.infoGen._qpos_cache is not cache and not torch.equal(a, c)
+
+
+def test_batch_position_dependence_q1():
+    """Quirk Q1: the same sample replicated in a batch gets different outputs (batch-axis recurrence)."""
+    net, sd, x, tp, *_ = make("tatt_g16_eval_n2")
+    xx, tt = x[:1].repeat(3, 1, 1, 1).to(DEV), tp[:1].repeat(3, 1, 1, 1).to(DEV)
+    with torch.no_grad():
+        out, _ = net(xx, tt)
+    assert (out[0] - out[1]).abs().max().item() > 0
+
+
+def test_default_text_prior_only_for_single_image():
+    net, sd, x, tp, *_ = make("tatt_g16_eval_n2")
+    from oracle import tatt_oracle as orc
+    with torch.no_grad():
+        out, pw = net(x[:1].to(DEV))                              # ptflops-style probe: no text prior
+    o_out, o_pw, _ = orc.tsrn_tl_trans_forward(sd, x[:1], None, training=False)
+    assert relerr(out, o_out) <= 1e-3
+    with pytest.raises(RuntimeError):
+        net(x.to(DEV))                                            # reference also fails for N > 1
+
+
+def test_train_mode_with_dropout_runs_and_is_seeded():
+    import tatt_b200
+    net, sd, x, tp, *_ = make("tatt_g16_stn_train_n3", zero_drop=False)
+    tatt_b200.manual_seed(5)
+    o1, _ = net(x.to(DEV), tp.to(DEV))
+    o1.mean().backward()
+    g1 = net.block2.conv1.weight.grad.clone()
+    assert torch.isfinite(o1).all() and torch.isfinite(g1).all()
+    o2, _ = net(x.to(DEV), tp.to(DEV))                            # counter advanced -> different masks
+    assert not torch.equal(o1, o2)
+    tatt_b200.manual_seed(5)
+    net.zero_grad()
+    # BN running stats moved, so only check the dropout stream restarts identically on a fresh copy
+    net2, *_ = make("tatt_g16_stn_train_n3", zero_drop=False)
+    tatt_b200.manual_seed(5)
+    o3, _ = net2(x.to(DEV), tp.to(DEV))
+    assert torch.equal(o1, o3)
+
+
+def test_cpu_tensor_raises_no_fallback():
+    import tatt_b200
+    net = tatt_b200.TSRN_TL_TRANS(width=128, height=32)
+    with pytest.raises(RuntimeError):
+        net.eval()(torch.rand(1, 4, 16, 64))
+
+
+def test_stn_at_g32_fails_like_reference():
+    import tatt_b200
+    net = tatt_b200.TSRN_TL_TRANS(width=256, height=64, STN=True).to(DEV).train()
+    with pytest.raises(RuntimeError, match="cannot be multiplied"):
+        net(torch.rand(2, 4, 32, 128, device=DEV), torch.rand(2, 37, 1, 26, device=DEV))
