@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py -- SR images/sec of the TATT hot path (BASELINE.json metric), one JSON line on rank 0.
+
+Workload (BASELINE.json configs[1]): TATT-TSRN = TSRN_TL_TRANS, LR 32x128 -> SR 64x256 ("G32": width=256,
+height=64, STN off -- the reference itself cannot run STN at this geometry), batch 64 per GPU, fp32,
+train mode (dropout 0.1 active), synthetic inputs, seed-1234 random-init weights.
+A "step" = forward + backward (+ one NCCL all-reduce of the flat gradient when N>1) + fused global-norm
+clip + Adam over the flat parameter buffer.  Weak scaling: per-GPU batch is fixed.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C-ABI)
+  python bench.py --impl reference ...                      the reference's CPU path (oracle port), rank 0 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "SR images/sec (32x128 LR, fwd+bwd)"
+UNIT = "images/s"
+ALG_FLOPS_FWD_BWD_G32 = 3.0 * 9.33e9     # ~9.33 GFLOP/img forward (RPE input-proj hoisted) x3 for fwd+bwd
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--geometry", default="g32", choices=["g32", "g16"])
+    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def geometry(name):
+    if name == "g32":
+        return dict(scale_factor=2, width=256, height=64, STN=False, mask=True), 32, 128
+    return dict(scale_factor=2, width=128, height=32, STN=True, mask=True), 16, 64
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [t.strip() for t in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(ctor_kw, h, w, sample_n, steps, warmup):
+    """The reference's own CPU path (oracle port: the same torch CPU ops in the same order), fwd+bwd,
+    dropout 0.1, all host threads."""
+    import tatt_b200
+    from oracle import tatt_oracle as orc
+    torch.manual_seed(1234)
+    net = tatt_b200.TSRN_TL_TRANS(**ctor_kw)          # parameter container only (CPU); never run
+    sd = orc.clone_sd(net.state_dict(), requires_grad=True)
+    x, tp = orc.synthetic_inputs(sample_n, h, w, seed=1234)
+    cores = torch.get_num_threads()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        for v in sd.values():
+            v.grad = None
+        out, _, _ = orc.tsrn_tl_trans_forward(sd, x, tp, training=True, stn=ctor_kw["STN"], dropout_p=0.1)
+        out.mean().backward()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    return {"value": sample_n * len(times) / tot, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d-image batch per step x %d steps of the same geometry (fwd+bwd, dropout 0.1), "
+                      "oracle port of the reference on torch CPU fp32" % (sample_n, len(times)),
+            "ms_per_step": 1e3 * tot / len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kw, h, w = geometry(args.geometry)
+    cb = cpu_baseline(kw, h, w, args.cpu_sample, args.steps, max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TSRN_TL_TRANS %s fwd+bwd, CPU sample batch %d" % (args.geometry, args.cpu_sample)},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def conv_roofline(dev, batch, h, w, peaks):
+    """Dominant kernel = the 3x3 64->64 implicit-GEMM convolution (11 forward instances per image plus their
+    data/weight gradients).  Algorithmic FLOPs per launch = 2*pixels*64*576; timed alone with CUDA events."""
+    from tatt_b200 import ops
+    x = torch.randn(batch, h, w, 64, device=dev)
+    wt = torch.randn(64, 64, 3, 3, device=dev) * 0.05
+    b = torch.zeros(64, device=dev)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)          # 256 MiB > L2
+    for _ in range(3):
+        ops.conv2d_fwd(x, wt, b, 1)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wtp = ops.conv_pack(wt, 64, 64, False)
+        y = torch.empty_like(x)
+        e0.record()
+        from tatt_b200 import _cabi
+        _cabi.call("tatt_conv2d_igemm", x.data_ptr(), wtp.data_ptr(), b.data_ptr(), y.data_ptr(), batch, h, w, 64, 64,
+                   3, 3, 1, 1, 0, ops._stream())
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    t = sum(ts) / len(ts)
+    flops = 2.0 * batch * h * w * 64 * 576
+    peak = peaks.get("bf16_tflops", 1590.0)
+    return {"bound": "tensor", "kernel": "gemm_kernel<128,64,16,8,4,IM2COL,KN> (conv3x3 64->64, fp32 FFMA)",
+            "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak,
+            "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks
+            else "fallback 1.59 PFLOP/s", "launch_ms": t * 1e3,
+            "note": "fp32 CUDA-core kernel measured against the bf16 tensor-core peak"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import tatt_b200
+    from tatt_b200 import _cabi, ops
+    from tatt_b200.train import Trainer
+    from oracle import tatt_oracle as orc   # only for the synthetic-input recipe and the cpu_baseline leg
+
+    kw, h, w = geometry(args.geometry)
+    torch.manual_seed(1234)
+    model = tatt_b200.TSRN_TL_TRANS(**kw).to(dev).train()
+    tatt_b200.manual_seed(1234 + rank)
+    trainer = Trainer(model)
+    B = args.batch
+    x_h, tp_h = orc.synthetic_inputs(B, h, w, seed=1234 + rank)
+    x_h, tp_h = x_h.pin_memory(), tp_h.pin_memory()
+    g_h = torch.randn(B, 4, 2 * h, 2 * w, generator=torch.Generator().manual_seed(7)) / (B * 4 * 4 * h * w)
+    x_d, tp_d, g_d = x_h.to(dev), tp_h.to(dev), g_h.to(dev)
+    metric_d = torch.zeros(1, device=dev)
+    metric_h = torch.zeros(1).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _cabi.launch_count
+        e0.record()
+        for _ in range(nsteps):
+            if e2e:
+                xs = x_h.to(dev, non_blocking=True)
+                ts_ = tp_h.to(dev, non_blocking=True)
+            else:
+                xs, ts_ = x_d, tp_d
+            out = trainer.step(xs, ts_, g_d)
+            if e2e:
+                _cabi.call("tatt_sqnorm", out.data_ptr(), out.numel(), metric_d.data_ptr(), 1, ops._stream())
+                metric_h.copy_(metric_d, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _cabi.launch_count - l0
+
+    timed(max(args.warmup, 3), False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = timed(args.steps, False)
+    clocks = sampler.stop()
+    timed(1, True)
+    ms_e2e, _ = timed(args.steps, True)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    value = B * world * args.steps / (ms * 1e-3)
+    e2e_v = B * world * args.steps / (ms_e2e * 1e-3)
+    roof = conv_roofline(dev, B, h, w, peaks)
+    roof["model_algorithmic_tflops"] = value * ALG_FLOPS_FWD_BWD_G32 / 1e12 if args.geometry == "g32" else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TSRN_TL_TRANS(width=%d,height=%d,STN=%s) fwd+bwd+clip+Adam, per-GPU batch %d, "
+                                   "train mode dropout 0.1" % (kw["width"], kw["height"], kw["STN"], B),
+                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": (x_h.numel() + tp_h.numel()) * 4, "d2h_bytes_per_step": 4},
+            "roofline": roof}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(kw, h, w, args.cpu_sample, 2, 1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -78,8 +78,15 @@ def last_error() -> str:
     return e.decode() if e else ""
 
 
+# kernels launched per entry-point call (everything not listed launches exactly one)
+_KERNELS = {"tatt_bn_stats": 2, "tatt_bn_bwd": 3, "tatt_memcpy_d2d": 0, "tatt_memset0": 0}
+launch_count = 0
+
+
 def call(name: str, *args):
     """Invoke an int-returning entry point; non-zero -> RuntimeError(tatt_last_error())."""
+    global launch_count
+    launch_count += _KERNELS.get(name, 1)
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, last_error()))

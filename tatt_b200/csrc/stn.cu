@@ -11,11 +11,11 @@ constexpr int NCP = 20;       // control points
 constexpr int NK = NCP + 3;   // TPS basis size
 
 __device__ __forceinline__ void tps_mapping(const float* __restrict__ invK, const float* __restrict__ ctrl,
-                                            float (*Mm)[2]) {
+                                            double (*Mm)[2]) {
   if (threadIdx.x < NK * 2) {
     int k = threadIdx.x >> 1, xy = threadIdx.x & 1;
-    float a = 0.f;
-    for (int i = 0; i < NCP; ++i) a = fmaf(invK[k * NK + i], ctrl[i * 2 + xy], a);
+    double a = 0.0;   // the TPS system is ill-conditioned: accumulate the mapping in double
+    for (int i = 0; i < NCP; ++i) a += (double)invK[k * NK + i] * (double)ctrl[i * 2 + xy];
     Mm[k][xy] = a;
   }
 }
@@ -45,21 +45,22 @@ __device__ __forceinline__ float4 fetch4(const float* __restrict__ img, int y, i
 __global__ void tps_sample_fwd_kernel(const float* __restrict__ X, const float* __restrict__ ctrl,
                                       const float* __restrict__ invK, const float* __restrict__ repr,
                                       float* __restrict__ OUT, float* __restrict__ SRC, int H, int W) {
-  __shared__ float Mm[NK][2];
+  __shared__ double Mm[NK][2];
   const int n = blockIdx.y;
   tps_mapping(invK, ctrl + (long long)n * NCP * 2, Mm);
   __syncthreads();
   const int HW = H * W;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
-  float sx = 0.f, sy = 0.f;
+  double sxd = 0.0, syd = 0.0;
   const float* rp = repr + (long long)p * NK;
 #pragma unroll
   for (int k = 0; k < NK; ++k) {
-    float r = __ldg(rp + k);
-    sx = fmaf(r, Mm[k][0], sx);
-    sy = fmaf(r, Mm[k][1], sy);
+    double r = (double)__ldg(rp + k);
+    sxd += r * Mm[k][0];
+    syd += r * Mm[k][1];
   }
+  const float sx = (float)sxd, sy = (float)syd;
   if (SRC) {
     SRC[((long long)n * HW + p) * 2 + 0] = sx;
     SRC[((long long)n * HW + p) * 2 + 1] = sy;
@@ -83,7 +84,7 @@ __global__ void tps_sample_bwd_kernel(const float* __restrict__ X, const float* 
                                       const float* __restrict__ invK, const float* __restrict__ repr,
                                       const float* __restrict__ dOUT, float* __restrict__ dctrl, int H, int W) {
   extern __shared__ float dsrc[];
-  __shared__ float Mm[NK][2];
+  __shared__ double Mm[NK][2];
   __shared__ float dM[NK][2];
   const int n = blockIdx.x;
   const int HW = H * W;
@@ -91,14 +92,15 @@ __global__ void tps_sample_bwd_kernel(const float* __restrict__ X, const float* 
   __syncthreads();
   const float* img = X + (long long)n * HW * 4;
   for (int p = threadIdx.x; p < HW; p += blockDim.x) {
-    float sx = 0.f, sy = 0.f;
+    double sxd = 0.0, syd = 0.0;
     const float* rp = repr + (long long)p * NK;
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
-      float r = __ldg(rp + k);
-      sx = fmaf(r, Mm[k][0], sx);
-      sy = fmaf(r, Mm[k][1], sy);
+      double r = (double)__ldg(rp + k);
+      sxd += r * Mm[k][0];
+      syd += r * Mm[k][1];
     }
+    const float sx = (float)sxd, sy = (float)syd;
     Bilin b = bilin_setup(sx, sy, H, W);
     float4 i00 = fetch4(img, b.y0, b.x0, H, W), i01 = fetch4(img, b.y0, b.x0 + 1, H, W);
     float4 i10 = fetch4(img, b.y0 + 1, b.x0, H, W), i11 = fetch4(img, b.y0 + 1, b.x0 + 1, H, W);

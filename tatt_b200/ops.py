@@ -369,6 +369,7 @@ class DeviceRNG:
     """{seed, counter} in device memory so dropout is CUDA-graph safe.  `snapshot()` copies the state
     for one forward call (its backward re-derives the same masks) and advances the counter."""
     _per_device = {}
+    _seed = None            # set by manual_seed(); None -> torch.initial_seed() at first use
 
     def __init__(self, device: torch.device, seed: int):
         self.state = torch.tensor([seed & ((1 << 63) - 1), 0], dtype=torch.int64, device=device)
@@ -377,11 +378,12 @@ class DeviceRNG:
     def get(cls, device: torch.device) -> "DeviceRNG":
         key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
         if key not in cls._per_device:
-            cls._per_device[key] = DeviceRNG(device, torch.initial_seed())
+            cls._per_device[key] = DeviceRNG(device, torch.initial_seed() if cls._seed is None else cls._seed)
         return cls._per_device[key]
 
     @classmethod
     def manual_seed(cls, seed: int) -> None:
+        cls._seed = seed
         for r in cls._per_device.values():
             r.state.copy_(torch.tensor([seed & ((1 << 63) - 1), 0], dtype=torch.int64))
 

@@ -1,0 +1,113 @@
+"""Data-parallel training step around the hot path (SURVEY 8e + 8f-3).
+
+One process per GPU; the batch is sharded on N; the only exchange is ONE all-reduce of the flat fp32
+gradient bucket (NCCL over NVLink on GPUs, gloo in the CPU tests).  Parameters that never receive a
+gradient (the 14 dead Q3 tensors) are not part of the bucket.  After the all-reduce the global-norm clip
+(clip_grad_norm_(., 0.25), interfaces/super_resolution.py:1083-1085) and Adam(lr 1e-3, betas (0.5, 0.999))
+(interfaces/base.py:557-558) run as one fused CUDA kernel over the flat parameter buffer.
+
+BatchNorm statistics stay per-rank, like each replica of the reference's nn.DataParallel (base.py:390):
+an N-way run reproduces N reference replicas at batch N_local, not one reference run at N_local*world.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+Tensor = torch.Tensor
+
+
+def shard_batch(n_global: int, rank: int, world: int) -> Tuple[int, int]:
+    """[start, stop) of rank's slice of a global batch (contiguous, sizes differ by at most 1)."""
+    base, rem = divmod(n_global, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class GradBucket:
+    """Flat fp32 views of the parameters that receive gradients.  Host-side logic only (layout,
+    packing, the collective); device-agnostic so it is covered by gloo tests on CPU."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], flatten_params: bool = True):
+        self.params: List[torch.nn.Parameter] = list(params)
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4            # keep every slice 16-byte aligned
+        self.numel = off
+        dev = self.params[0].device
+        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_param: Optional[Tensor] = None
+        if flatten_params:
+            self.flat_param = torch.zeros(off, dtype=torch.float32, device=dev)
+            for p, o in zip(self.params, self.offsets):
+                self.flat_param[o:o + p.numel()].copy_(p.data.reshape(-1))
+                p.data = self.flat_param[o:o + p.numel()].view(p.shape)
+
+    @classmethod
+    def from_model_after_backward(cls, model: torch.nn.Module, flatten_params: bool = True) -> "GradBucket":
+        return cls([p for p in model.parameters() if p.grad is not None], flatten_params)
+
+    def pack(self) -> Tensor:
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None:
+                raise RuntimeError("parameter of the gradient bucket has no gradient this step")
+            self.flat_grad[o:o + p.numel()].copy_(p.grad.reshape(-1))
+        return self.flat_grad
+
+    def allreduce_mean(self, group=None) -> Tensor:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
+            self.flat_grad.div_(dist.get_world_size(group))
+        return self.flat_grad
+
+    def unpack_into_grads(self) -> None:
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+
+class Trainer:
+    """fwd + bwd + (all-reduce) + fused clip/Adam for TSRN_TL_TRANS / TSRN on CUDA."""
+
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.5, 0.999), eps: float = 1e-8,
+                 max_norm: float = 0.25, group=None):
+        self.model, self.lr, self.betas, self.eps, self.max_norm, self.group = model, lr, betas, eps, max_norm, group
+        self.bucket: Optional[GradBucket] = None
+        self.step_count = 0
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def forward_backward(self, x: Tensor, text_emb: Optional[Tensor], grad_out: Tensor):
+        for p in self.model.parameters():
+            p.grad = None
+        res = self.model(x, text_emb) if text_emb is not None else self.model(x)
+        out = res[0] if isinstance(res, tuple) else res
+        torch.autograd.backward([out], [grad_out])
+        return out
+
+    def optimizer_step(self) -> Tensor:
+        from . import _cabi, ops
+        if self.bucket is None:
+            self.bucket = GradBucket.from_model_after_backward(self.model)
+            b = self.bucket
+            self.m = torch.zeros_like(b.flat_grad)
+            self.v = torch.zeros_like(b.flat_grad)
+            self.sq = torch.zeros(1, dtype=torch.float32, device=b.flat_grad.device)
+        b = self.bucket
+        g = b.pack()
+        if self.world > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        self.step_count += 1
+        st = ops._stream()
+        # sum(g^2) of the SUMMED gradient; the 1/world averaging is folded into the fused step
+        _cabi.call("tatt_sqnorm", g.data_ptr(), b.numel, self.sq.data_ptr(), 1, st)
+        _cabi.call("tatt_adam_clip_step", b.flat_param.data_ptr(), g.data_ptr(), self.m.data_ptr(),
+                   self.v.data_ptr(), b.numel, self.sq.data_ptr(), self.max_norm, self.lr, self.betas[0],
+                   self.betas[1], self.eps, self.step_count, 1.0 / self.world, st)
+        return self.sq
+
+    def step(self, x: Tensor, text_emb: Optional[Tensor], grad_out: Tensor):
+        out = self.forward_backward(x, text_emb, grad_out)
+        self.optimizer_step()
+        return out

@@ -1,7 +1,11 @@
 """End-to-end parity of the drop-in modules (CUDA, through the C-ABI) against the oracle restatement and
 the committed reference fixtures.  Stated tolerances (fp32): outputs / intermediates <= 1e-3 relative to
-the tensor's max-abs (north_star bound); parameter gradients <= 2e-3 relative to the gradient's max-abs
-(split-K / atomic accumulation order differs from the CPU's)."""
+the tensor's max-abs (north_star bound) against the fp32 oracle.  Parameter gradients: <= 2e-3 relative to
+the gradient's max-abs (plus an absolute floor of 1e-5 x the largest gradient in the model, for the conv biases
+in front of a train-mode BatchNorm whose true gradient is exactly 0) against the oracle evaluated in FLOAT64.
+Float64 because the reference's own fp32 backward is noisy on this path: with STN on, its fp32 gradients deviate
+from its fp64 gradients by up to 1.2e-2 (block1.0.bias; measured), so fp32-vs-fp32 would compare
+two rounding noises.  The committed fp32 reference fixtures are still checked, at 3e-2 for gradients."""
 import pytest
 import torch
 
@@ -33,8 +37,20 @@ def make(case, zero_drop=True):
     return net.to(DEV), sd, x, tp, cls, kw, N, training
 
 
+def to_dtype(sd, dt):
+    out = {}
+    for k, v in sd.items():
+        t = v.detach().clone().to(dt) if v.is_floating_point() else v.detach().clone()
+        if v.requires_grad:
+            t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
 def run_oracle(cls, kw, sd, x, tp, training):
     from oracle import tatt_oracle as orc
+    dt = next(v.dtype for v in sd.values() if v.is_floating_point())
+    x, tp = x.to(dt), tp.to(dt)
     if cls == "TSRN":
         out, block = orc.tsrn_forward(sd, x, training=training, stn=kw["STN"])
         return out, None, block
@@ -50,6 +66,7 @@ def test_forward_backward_vs_oracle_and_golden(case):
         out, aux = net(xo), None
     else:
         out, aux = net(xo, tp.to(DEV))
+    sd64 = to_dtype(sd, torch.float64)
     o_out, o_aux, o_block = run_oracle(cls, kw, sd, x, tp, training)
     assert out.shape == o_out.shape and out.dtype == torch.float32
     assert relerr(out, o_out) <= 1e-3, "output vs oracle: %.3e" % relerr(out, o_out)
@@ -75,30 +92,31 @@ def test_forward_backward_vs_oracle_and_golden(case):
     gen = torch.Generator().manual_seed(99)
     wgt = torch.randn(out.shape, generator=gen)
     (out * wgt.to(DEV)).sum().backward()
-    (o_out * wgt).sum().backward()
+    o64, _, _ = run_oracle(cls, kw, sd64, x, tp, training)
+    (o64 * wgt.double()).sum().backward()
+    G = max(v.grad.abs().max().item() for v in sd64.values() if v.requires_grad and v.grad is not None)
     worst = ("", 0.0)
     for n, p in net.named_parameters():
-        og = sd[n].grad
+        og = sd64[n].grad
         ref = fx["grads"][n]
         if ref is None:                      # Q3 dead parameters never receive a gradient
             assert p.grad is None, n
             assert og is None or og.abs().max().item() == 0
             continue
         assert p.grad is not None, n
-        if og.abs().max().item() == 0:
-            assert p.grad.abs().max().item() <= 1e-6, n
-            continue
-        e = relerr(p.grad, og)
-        if e > worst[1]:
-            worst = (n, e)
-        assert e <= 2e-3, "grad %s vs oracle: %.3e" % (n, e)
-        gu.check_summary("grad " + n, p.grad, ref, 2e-3)
+        err = (p.grad.detach().double().cpu() - og).abs().max().item()
+        bound = 2e-3 * og.abs().max().item() + 1e-5 * G
+        if err / bound > worst[1]:
+            worst = (n, err / bound)
+        assert err <= bound, "grad %s vs fp64 oracle: err %.3e > bound %.3e (max %.3e)" % (
+            n, err, bound, og.abs().max().item())
+        gu.check_summary("grad " + n, p.grad, ref, 3e-2, atol=1e-5 * G)
     # BatchNorm running statistics were updated exactly like torch does
     for n, b in net.named_buffers():
         if "running" in n or "num_batches" in n:
             assert relerr(b.float(), sd[n].float()) <= 1e-4, n
             gu.check_summary("buffer " + n, b.float(), fx["buffers"][n], 1e-4)
-    print("worst grad", worst)
+    print("worst grad (err/bound)", worst)
 
 
 def test_eval_repeatable_and_qpos_cache():
@@ -137,19 +155,17 @@ def test_default_text_prior_only_for_single_image():
 
 def test_train_mode_with_dropout_runs_and_is_seeded():
     import tatt_b200
-    net, sd, x, tp, *_ = make("tatt_g16_stn_train_n3", zero_drop=False)
     tatt_b200.manual_seed(5)
+    net, sd, x, tp, *_ = make("tatt_g16_stn_train_n3", zero_drop=False)
     o1, _ = net(x.to(DEV), tp.to(DEV))
     o1.mean().backward()
     g1 = net.block2.conv1.weight.grad.clone()
     assert torch.isfinite(o1).all() and torch.isfinite(g1).all()
     o2, _ = net(x.to(DEV), tp.to(DEV))                            # counter advanced -> different masks
     assert not torch.equal(o1, o2)
+    # BN running stats moved, so check the dropout stream restarts identically on a fresh copy
     tatt_b200.manual_seed(5)
-    net.zero_grad()
-    # BN running stats moved, so only check the dropout stream restarts identically on a fresh copy
     net2, *_ = make("tatt_g16_stn_train_n3", zero_drop=False)
-    tatt_b200.manual_seed(5)
     o3, _ = net2(x.to(DEV), tp.to(DEV))
     assert torch.equal(o1, o3)
 

@@ -282,9 +282,20 @@ def test_tps_grid_sample():
     cd = ctrl.detach().to(dev()).contiguous()
     invk, rep = tps.inverse_kernel.to(dev()), tps.target_coordinate_repr.to(dev())
     od, sd = ops.tps_sample_fwd(xd, cd, invk, rep, want_src=True)
-    close(sd, src, tol=1e-4, name="tps src"); close(ops.nhwc_to_nchw(od, 4), out, tol=2e-4, name="grid_sample")
+    # The TPS system is ill-conditioned (|inverse_kernel| entries ~1e3): the reference's own fp32 result is only
+    # ~1e-3 from its fp64 result.  Tight check against float64 truth, loose check against the fp32 CPU run.
+    c64 = ctrl.detach().double().requires_grad_(True)
+    Y64 = torch.cat([c64, tps.padding_matrix.double().expand(N, 3, 2)], 1)
+    src64 = torch.matmul(tps.target_coordinate_repr.double(), torch.matmul(tps.inverse_kernel.double(), Y64))
+    out64 = F.grid_sample(x.double(), 2.0 * torch.clamp(src64.view(-1, H, W, 2), 0, 1) - 1.0, mode="bilinear",
+                          padding_mode="zeros", align_corners=False)
+    out64.backward(dout.double())
+    close(sd, src64, tol=2e-5, name="tps src vs fp64"); close(sd, src, tol=1e-4, name="tps src vs fp32")
+    close(ops.nhwc_to_nchw(od, 4), out64, tol=2e-4, name="grid_sample vs fp64")
+    close(ops.nhwc_to_nchw(od, 4), out, tol=3e-3, name="grid_sample vs fp32")
     dc = ops.tps_sample_bwd(xd, cd, invk, rep, ops.nchw_to_nhwc(dout.to(dev()), 4))
-    close(dc, ctrl.grad, tol=2e-3, name="tps dctrl")
+    close(dc, c64.grad, tol=1e-3, name="tps dctrl vs fp64")
+    close(dc, ctrl.grad, tol=2e-2, name="tps dctrl vs fp32")
 
 
 def test_adam_clip_step():
