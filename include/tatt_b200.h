@@ -127,9 +127,10 @@ int tatt_tps_sample_bwd(const float* X, const float* ctrl, const float* invK, co
 
 /* ---- gradient step on a flat buffer: clip_grad_norm_(0.25) + Adam, interfaces/super_resolution.py:1083-1085 */
 int tatt_sqnorm(const float* x, long long n, float* out, int zero_first, void* stream);
+/* step_state: DEVICE {unused, step>=1} (advance it with tatt_rng_advance before the call) */
 int tatt_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, const float* sqnorm,
-                        float max_norm, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
-                        void* stream);
+                        float max_norm, float lr, float beta1, float beta2, float eps,
+                        const unsigned long long* step_state, float grad_scale, void* stream);
 
 /* ---- plumbing ------------------------------------------------------------------------------------------- */
 int tatt_memcpy_d2d(void* dst, const void* src, long long bytes, void* stream);

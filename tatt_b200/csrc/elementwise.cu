@@ -238,8 +238,11 @@ __global__ void sqnorm_kernel(const float* __restrict__ x, long long n, float* _
 // sqnorm[0] holds sum(g^2) over the whole buffer (already all-reduced and averaged grads).
 __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long long n, const float* __restrict__ sqnorm,
-                                 float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2,
-                                 float grad_scale) {
+                                 float max_norm, float lr, float b1, float b2, float eps,
+                                 const unsigned long long* __restrict__ step_state, float grad_scale) {
+  // step counter lives in device memory (CUDA-graph replays must see it advance)
+  const float stepf = (float)step_state[1];
+  const float bc1 = 1.f - powf(b1, stepf), bc2 = 1.f - powf(b2, stepf);
   float coef = 1.f;
   if (max_norm > 0.f) {
     float tn = sqrtf(sqnorm[0]) * grad_scale;
@@ -395,12 +398,12 @@ int tatt_sqnorm(const float* x, long long n, float* out, int zero_first, void* s
 }
 
 int tatt_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, const float* sqnorm,
-                        float max_norm, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
-                        void* stream) {
+                        float max_norm, float lr, float beta1, float beta2, float eps,
+                        const unsigned long long* step_state, float grad_scale, void* stream) {
   if (n <= 0) return 0;
-  float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  TATT_REQUIRE(step_state != nullptr, "adam_clip_step: step_state (device {unused, step}) is required");
   adam_clip_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sqnorm, max_norm, lr, beta1,
-                                                                   beta2, eps, bc1, bc2, grad_scale);
+                                                                   beta2, eps, step_state, grad_scale);
   TATT_LAUNCH_CHECK("adam_clip_kernel");
   return 0;
 }

@@ -69,13 +69,12 @@ class GradBucket:
 
 
 class Trainer:
-    """fwd + bwd + (all-reduce) + fused clip/Adam for TSRN_TL_TRANS / TSRN on CUDA."""
+    """fwd + bwd + (all-reduce) + fused clip/Adam for TSRN_TL_TRANS / TSRN on CUDA (eager launches)."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.5, 0.999), eps: float = 1e-8,
                  max_norm: float = 0.25, group=None):
         self.model, self.lr, self.betas, self.eps, self.max_norm, self.group = model, lr, betas, eps, max_norm, group
         self.bucket: Optional[GradBucket] = None
-        self.step_count = 0
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 
     def forward_backward(self, x: Tensor, text_emb: Optional[Tensor], grad_out: Tensor):
@@ -86,28 +85,85 @@ class Trainer:
         torch.autograd.backward([out], [grad_out])
         return out
 
-    def optimizer_step(self) -> Tensor:
-        from . import _cabi, ops
+    def _ensure_bucket(self) -> GradBucket:
         if self.bucket is None:
             self.bucket = GradBucket.from_model_after_backward(self.model)
             b = self.bucket
             self.m = torch.zeros_like(b.flat_grad)
             self.v = torch.zeros_like(b.flat_grad)
             self.sq = torch.zeros(1, dtype=torch.float32, device=b.flat_grad.device)
-        b = self.bucket
-        g = b.pack()
+            self.step_state = torch.zeros(2, dtype=torch.int64, device=b.flat_grad.device)   # {unused, step}
+        return self.bucket
+
+    def _allreduce(self) -> None:
         if self.world > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
-        self.step_count += 1
-        st = ops._stream()
-        # sum(g^2) of the SUMMED gradient; the 1/world averaging is folded into the fused step
+            dist.all_reduce(self.bucket.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _update_kernels(self) -> None:
+        """sum(g^2) of the SUMMED gradient, then clip + Adam; the 1/world averaging is folded in."""
+        from . import _cabi, ops
+        b, st = self.bucket, ops._stream()
+        g = b.flat_grad
         _cabi.call("tatt_sqnorm", g.data_ptr(), b.numel, self.sq.data_ptr(), 1, st)
+        _cabi.call("tatt_rng_advance", self.step_state.data_ptr(), st)
         _cabi.call("tatt_adam_clip_step", b.flat_param.data_ptr(), g.data_ptr(), self.m.data_ptr(),
                    self.v.data_ptr(), b.numel, self.sq.data_ptr(), self.max_norm, self.lr, self.betas[0],
-                   self.betas[1], self.eps, self.step_count, 1.0 / self.world, st)
+                   self.betas[1], self.eps, self.step_state.data_ptr(), 1.0 / self.world, st)
+
+    def optimizer_step(self) -> Tensor:
+        self._ensure_bucket().pack()
+        self._allreduce()
+        self._update_kernels()
         return self.sq
 
     def step(self, x: Tensor, text_emb: Optional[Tensor], grad_out: Tensor):
         out = self.forward_backward(x, text_emb, grad_out)
         self.optimizer_step()
         return out
+
+
+class GraphedTrainer(Trainer):
+    """The same step captured into CUDA graphs for fixed shapes: graph 1 = forward + backward + gradient
+    packing, (eager NCCL all-reduce when world > 1), graph 2 = grad-norm + clip + Adam.  Three host launches
+    per step instead of ~800; dropout and the Adam step counter read device-resident state, so replays
+    advance them."""
+
+    def __init__(self, model: torch.nn.Module, x_shape, text_shape, out_shape, **kw):
+        super().__init__(model, **kw)
+        dev = next(model.parameters()).device
+        self.x = torch.zeros(x_shape, dtype=torch.float32, device=dev)
+        self.text = torch.zeros(text_shape, dtype=torch.float32, device=dev) if text_shape is not None else None
+        self.grad_out = torch.zeros(out_shape, dtype=torch.float32, device=dev)
+        self.graph_fb = self.graph_opt = None
+        self.out: Optional[Tensor] = None
+
+    def capture(self, warmup: int = 2) -> None:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                Trainer.step(self, self.x, self.text, self.grad_out)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self.out = self.forward_backward(self.x, self.text, self.grad_out)
+            self.bucket.pack()
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
+            self._update_kernels()
+
+    def step(self, x: Optional[Tensor] = None, text_emb: Optional[Tensor] = None, grad_out: Optional[Tensor] = None):
+        """Inputs may live on the host (pinned) or the device; None -> reuse the static buffers."""
+        if self.graph_fb is None:
+            self.capture()
+        if x is not None and x is not self.x:
+            self.x.copy_(x, non_blocking=True)
+        if text_emb is not None and text_emb is not self.text:
+            self.text.copy_(text_emb, non_blocking=True)
+        if grad_out is not None and grad_out is not self.grad_out:
+            self.grad_out.copy_(grad_out, non_blocking=True)
+        self.graph_fb.replay()
+        self._allreduce()
+        self.graph_opt.replay()
+        return self.out

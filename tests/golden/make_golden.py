@@ -44,6 +44,25 @@ def main():
             (out * wgt).sum().backward()
             fx["grads"] = {n: (None if p.grad is None else gu.summarize(p.grad, nsamp=8))
                            for n, p in net.named_parameters()}
+            # the same backward with the reference evaluated in float64, and the reference's own
+            # fp32-vs-fp64 deviation per parameter (its rounding noise: ReLU / max-pool flips, TPS conditioning)
+            import copy
+            torch.manual_seed(gu.SEED)
+            n64 = getattr(ref, cls)(**kw)
+            rh.zero_dropout(n64)
+            rh.perturb_(n64)
+            n64 = n64.double().train(True)
+            o64 = n64(x.double()) if cls == "TSRN" else n64(x.double(), tp.double())[0]
+            (o64 * wgt.double()).sum().backward()
+            g32 = dict(net.named_parameters())
+            fx["grads64"], fx["noise"] = {}, {}
+            for n, p in n64.named_parameters():
+                if p.grad is None:
+                    fx["grads64"][n] = None
+                    continue
+                fx["grads64"][n] = gu.summarize(p.grad, nsamp=8)
+                fx["noise"][n] = (g32[n].grad.double() - p.grad).abs().max().item()
+            fx["gmax"] = max(p.grad.abs().max().item() for p in n64.parameters() if p.grad is not None)
             fx["buffers"] = {n: gu.summarize(b.float(), nsamp=4) for n, b in net.named_buffers()
                              if "running" in n or "num_batches" in n}
         path = os.path.join(gu.GOLDEN_DIR, name + ".pt")

@@ -5,7 +5,9 @@ the gradient's max-abs (plus an absolute floor of 1e-5 x the largest gradient in
 in front of a train-mode BatchNorm whose true gradient is exactly 0) against the oracle evaluated in FLOAT64.
 Float64 because the reference's own fp32 backward is noisy on this path: with STN on, its fp32 gradients deviate
 from its fp64 gradients by up to 1.2e-2 (block1.0.bias; measured), so fp32-vs-fp32 would compare
-two rounding noises.  The committed fp32 reference fixtures are still checked, at 3e-2 for gradients."""
+two rounding noises; the bound is widened by 3x that measured per-parameter deviation (ReLU / max-pool flips
+and the ill-conditioned TPS solve make the fp32 backward itself non-smooth).  The committed fixtures carry the
+reference's float64 gradients and its fp32 noise, and are checked with the same bound."""
 import pytest
 import torch
 
@@ -92,7 +94,8 @@ def test_forward_backward_vs_oracle_and_golden(case):
     gen = torch.Generator().manual_seed(99)
     wgt = torch.randn(out.shape, generator=gen)
     (out * wgt.to(DEV)).sum().backward()
-    o64, _, _ = run_oracle(cls, kw, sd64, x, tp, training)
+    (o_out * wgt).sum().backward()
+    o64 = run_oracle(cls, kw, sd64, x, tp, training)[0]
     (o64 * wgt.double()).sum().backward()
     G = max(v.grad.abs().max().item() for v in sd64.values() if v.requires_grad and v.grad is not None)
     worst = ("", 0.0)
@@ -105,12 +108,13 @@ def test_forward_backward_vs_oracle_and_golden(case):
             continue
         assert p.grad is not None, n
         err = (p.grad.detach().double().cpu() - og).abs().max().item()
-        bound = 2e-3 * og.abs().max().item() + 1e-5 * G
+        noise = (sd[n].grad.double() - og).abs().max().item()        # the fp32 reference's own deviation
+        bound = 2e-3 * og.abs().max().item() + 3.0 * noise + 1e-5 * G
         if err / bound > worst[1]:
             worst = (n, err / bound)
         assert err <= bound, "grad %s vs fp64 oracle: err %.3e > bound %.3e (max %.3e)" % (
             n, err, bound, og.abs().max().item())
-        gu.check_summary("grad " + n, p.grad, ref, 3e-2, atol=1e-5 * G)
+        gu.check_summary("grad " + n, p.grad, fx["grads64"][n], 2e-3, atol=3.0 * fx["noise"][n] + 1e-5 * fx["gmax"])
     # BatchNorm running statistics were updated exactly like torch does
     for n, b in net.named_buffers():
         if "running" in n or "num_batches" in n:
@@ -182,3 +186,30 @@ def test_stn_at_g32_fails_like_reference():
     net = tatt_b200.TSRN_TL_TRANS(width=256, height=64, STN=True).to(DEV).train()
     with pytest.raises(RuntimeError, match="cannot be multiplied"):
         net(torch.rand(2, 4, 32, 128, device=DEV), torch.rand(2, 37, 1, 26, device=DEV))
+
+
+def test_graphed_trainer_matches_eager_trainer():
+    """CUDA-graph replay of fwd+bwd+clip+Adam == eager launches (dropout off so both are deterministic)."""
+    from tatt_b200.train import GraphedTrainer, Trainer
+    nets = []
+    for _ in range(2):
+        net, sd, x, tp, cls, kw, N, training = make("tatt_g16_stn_train_n3")
+        nets.append(net)
+    g = torch.randn(N, 4, 32, 128, generator=torch.Generator().manual_seed(3)).to(DEV) * 1e-3
+    xe, te = x.to(DEV), tp.to(DEV)
+    eager = Trainer(nets[0])
+    graphed = GraphedTrainer(nets[1], tuple(x.shape), tuple(tp.shape), tuple(g.shape))
+    graphed.x.copy_(xe); graphed.text.copy_(te); graphed.grad_out.copy_(g)
+    graphed.capture(warmup=2)                         # 2 eager warm-up steps (these update the weights too)
+    for _ in range(2):
+        eager.step(xe, te, g)
+    for _ in range(3):                                # 3 more steps each
+        eager.step(xe, te, g)
+        graphed.step(x.pin_memory(), tp.pin_memory())
+    torch.cuda.synchronize()
+    assert int(graphed.step_state[1].item()) == int(eager.step_state[1].item()) == 5
+    pa, pb = eager.bucket.flat_param, graphed.bucket.flat_param
+    assert (pa - pb).abs().max().item() <= 1e-5 * pa.abs().max().item()
+    for (n1, b1), (n2, b2) in zip(nets[0].named_buffers(), nets[1].named_buffers()):
+        if "num_batches" in n1:
+            assert torch.equal(b1, b2), n1

@@ -306,9 +306,11 @@ def test_adam_clip_step():
     opt = torch.optim.Adam([p], lr=1e-3, betas=(0.5, 0.999))
     pd, gd = p0.to(dev()), gr.to(dev())
     m, v, sq = torch.zeros_like(pd), torch.zeros_like(pd), torch.zeros(1, device=dev())
+    state = torch.zeros(2, dtype=torch.int64, device=dev())
     for step in (1, 2, 3):
         torch.nn.utils.clip_grad_norm_([p], 0.25); opt.step(); p.grad = gr.clone()
         _cabi.call("tatt_sqnorm", gd.data_ptr(), n, sq.data_ptr(), 1, ops._stream())
+        _cabi.call("tatt_rng_advance", state.data_ptr(), ops._stream())
         _cabi.call("tatt_adam_clip_step", pd.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, sq.data_ptr(),
-                   0.25, 1e-3, 0.5, 0.999, 1e-8, step, 1.0, ops._stream())
+                   0.25, 1e-3, 0.5, 0.999, 1e-8, state.data_ptr(), 1.0, ops._stream())
     close(pd, p, tol=1e-5, name="adam")
