@@ -11,52 +11,11 @@
 // Replaces, on the hot path, the cuDNN conv / cuBLAS GEMM calls PyTorch dispatches for the
 // reference's nn.Conv2d / nn.Linear / GRU projections (model/tsrn.py:596-623, 876-888, 1070-1071;
 // model/transformer_v2.py:453-458, 785-790).
+#include <stdlib.h>
 #include "common.cuh"
+#include "gemm_params.cuh"
 
 namespace {
-
-struct FastDiv {
-  unsigned mul, shr, d;
-};
-static FastDiv make_fd(unsigned d) {
-  FastDiv f;
-  f.d = d;
-  if (d <= 1) {
-    f.mul = 0;
-    f.shr = 0;
-    f.d = 1;
-    return f;
-  }
-  int lg = 31 - __builtin_clz(d);
-  if (d & (d - 1)) lg += 1;  // ceil(log2(d))
-  int p = 31 + lg;
-  unsigned long long m = ((1ull << p) + d - 1) / d;
-  f.mul = (unsigned)m;
-  f.shr = (unsigned)(p - 32);
-  return f;
-}
-__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
-  return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
-}
-
-enum { A_ROW = 0, A_COL = 1, A_IM2COL = 2, A_IM2COL_T = 3 };
-enum { B_KN = 0, B_NK = 1 };
-enum { F_ACCUM = 1, F_RELU = 2, F_ATOMIC = 4, F_VECA = 8, F_VECB = 16, F_VECC = 32 };
-
-struct GemmP {
-  const float* A;
-  const float* B;
-  float* C;
-  const float* bias;
-  int M, N, K;
-  long long lda, ldb, ldc;
-  long long sA, sB, sC, sBias;
-  int batch, splitk, kper;
-  int flags;
-  // conv geometry (IM2COL modes): X[nimg][cH][cW][cC]
-  int cH, cW, cC, KH, KW, padH, padW;
-  FastDiv fdHW, fdW, fdC, fdKW;
-};
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -437,6 +396,16 @@ static int run_gemm(GemmP p, int amode, int bmode, bool want_split, cudaStream_t
   if (vb) fl |= F_VECB;
   if (vc) fl |= F_VECC;
   p.flags = fl;
+
+  // tensor-core path first (tc_gemm.cu); -1 = shape not eligible -> FFMA kernels below
+  static const bool tc_on = []() {
+    const char* e = getenv("TATT_TC");
+    return !(e && e[0] == '0');
+  }();
+  if (tc_on) {
+    int rc = tatt_tc_gemm_launch(p, amode, bmode, want_split, st);
+    if (rc >= 0) return rc;
+  }
 
   // config selection
   int cfg;  // 0: 128x64 (256 thr)  1: 64x64 (256 thr)  2: 256x4 (32 thr)

@@ -1,0 +1,51 @@
+// Parameter block shared by the FFMA (gemm.cu) and tcgen05 (tc_gemm.cu) GEMM / implicit-GEMM engines.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct FastDiv {
+  unsigned mul, shr, d;
+};
+static inline FastDiv make_fd(unsigned d) {
+  FastDiv f;
+  f.d = d;
+  if (d <= 1) {
+    f.mul = 0;
+    f.shr = 0;
+    f.d = 1;
+    return f;
+  }
+  int lg = 31 - __builtin_clz(d);
+  if (d & (d - 1)) lg += 1;  // ceil(log2(d))
+  int p = 31 + lg;
+  unsigned long long m = ((1ull << p) + d - 1) / d;
+  f.mul = (unsigned)m;
+  f.shr = (unsigned)(p - 32);
+  return f;
+}
+__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
+  return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
+
+enum { A_ROW = 0, A_COL = 1, A_IM2COL = 2, A_IM2COL_T = 3 };
+enum { B_KN = 0, B_NK = 1 };
+enum { F_ACCUM = 1, F_RELU = 2, F_ATOMIC = 4, F_VECA = 8, F_VECB = 16, F_VECC = 32 };
+
+struct GemmP {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;
+  int M, N, K;
+  long long lda, ldb, ldc;
+  long long sA, sB, sC, sBias;
+  int batch, splitk, kper;
+  int flags;
+  // conv geometry (IM2COL modes): X[nimg][cH][cW][cC]
+  int cH, cW, cC, KH, KW, padH, padW;
+  FastDiv fdHW, fdW, fdC, fdKW;
+};
+
+
+// tcgen05 path (tc_gemm.cu); returns 0 on success, -1 if the shape is not eligible (caller falls through to FFMA)
+int tatt_tc_gemm_launch(GemmP p, int amode, int bmode, bool want_split, cudaStream_t st);

@@ -340,6 +340,7 @@ def maxpool_bwd(x: Tensor, dout: Tensor, kh: int, kw: int) -> Tensor:
 def tps_sample_fwd(x: Tensor, ctrl: Tensor, invk: Tensor, repr_: Tensor, want_src: bool = False):
     n, h, w, c = x.shape
     assert c == 4
+    invk, repr_, ctrl = invk.contiguous(), repr_.contiguous(), ctrl.contiguous()   # torch.inverse is column-major
     out = torch.empty_like(x)
     src = empty(n, h * w, 2, like=x) if want_src else None
     _cabi.call("tatt_tps_sample_fwd", _p(x), _p(ctrl), _p(invk), _p(repr_), _p(out), _p(src), n, h, w, _stream())
@@ -348,6 +349,7 @@ def tps_sample_fwd(x: Tensor, ctrl: Tensor, invk: Tensor, repr_: Tensor, want_sr
 
 def tps_sample_bwd(x: Tensor, ctrl: Tensor, invk: Tensor, repr_: Tensor, dout: Tensor) -> Tensor:
     n, h, w, c = x.shape
+    invk, repr_, ctrl = invk.contiguous(), repr_.contiguous(), ctrl.contiguous()
     dctrl = torch.empty_like(ctrl)
     _cabi.call("tatt_tps_sample_bwd", _p(x), _p(ctrl), _p(invk), _p(repr_), _p(dout), _p(dctrl), n, h, w, _stream())
     return dctrl
