@@ -28,7 +28,7 @@ int tatt_arch(void);
  * model/tsrn.py:170,1070 ; model/transformer_v2.py:453-458,785-790,177 ; model/stn_head.py:49-53
  * amode: 0 A[M][K] row-major, 1 A given as [K][M].  bmode: 0 B[K][N], 1 B given as [N][K].
  * flags: 1 accumulate into C, 2 ReLU epilogue, 4 split-K with atomics (C must be zero, or add 64 to
- * have a dense C zeroed here).  batch > 1 strides A/B/C/bias by sA/sB/sC/sBias elements. */
+ * have a dense C zeroed here), 128 force the fp32 FFMA kernels instead of the tcgen05 bf16x3 path.  batch > 1 strides A/B/C/bias by sA/sB/sC/sBias elements. */
 int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* B, long long ldb, float* C,
               long long ldc, const float* bias, int M, int N, int K, int batch, long long sA, long long sB,
               long long sC, long long sBias, int flags, void* stream);
@@ -46,7 +46,18 @@ int tatt_conv_weight_unpack_grad(const float* dWt, float* dW, int Cout, int Cin,
 int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W, int Cin,
                       int Cout, int KH, int KW, int padH, int padW, int flags, void* stream);
 int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cin, int Cout,
-                      int KH, int KW, int padH, int padW, void* stream);
+                      int KH, int KW, int padH, int padW, int flags, void* stream);
+
+/* 9x9 convolution with <= 4 output channels (tsrn.py:623) as a K = KH*Cin, N = KW*CoP GEMM over the vertical
+ * taps (tatt_conv2d_igemm / tatt_conv2d_wgrad with KW=1) plus these horizontal shift-sum / shift-expand passes */
+int tatt_conv_kxexp_pack(const float* W, float* Wt, int Cout, int Cin, int KH, int KW, int CinP, int CoP,
+                         void* stream);
+int tatt_conv_kxexp_unpack_grad(const float* dWt, float* dW, int Cout, int Cin, int KH, int KW, int CinP, int CoP,
+                                void* stream);
+int tatt_conv_kxexp_reduce(const float* T, const float* bias, float* out, long long P, int W, int KW, int CoP,
+                           int padW, void* stream);
+int tatt_conv_kxexp_expand(const float* dOut, float* dT, long long P, int W, int KW, int CoP, int padW,
+                           void* stream);
 
 /* ---- BatchNorm (batch statistics over all rows of X[P][C]) with fused activation ----------------------
  * nn.BatchNorm2d/1d: model/tsrn.py:878,886,612 ; model/stn_head.py:19,51.  act: 0 none, 1 ReLU, 2 mish

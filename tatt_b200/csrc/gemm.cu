@@ -402,7 +402,7 @@ static int run_gemm(GemmP p, int amode, int bmode, bool want_split, cudaStream_t
     const char* e = getenv("TATT_TC");
     return !(e && e[0] == '0');
   }();
-  if (tc_on) {
+  if (tc_on && !p.no_tc) {
     int rc = tatt_tc_gemm_launch(p, amode, bmode, want_split, st);
     if (rc >= 0) return rc;
   }
@@ -488,6 +488,70 @@ __global__ void conv_unpack_grad_kernel(const float* __restrict__ dWt, float* __
   }
 }
 
+// "kx-expansion" of a KHxKW convolution with very few output channels (the 9x9 64->4 output conv):
+// T[p][kx*CoP+co] = sum_{ky,ci} X[p + (ky-padH, 0)][ci] * W[co][ci][ky][kx]   (a K = KH*Cin, N = KW*CoP GEMM),
+// out[y][x][co] = bias[co] + sum_kx T[y][x + kx - padW][kx*CoP+co]              (horizontal shift-sum).
+__global__ void kxexp_pack_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Cout, int Cin, int KH,
+                                  int KW, int CinP, int CoP) {
+  long long total = (long long)KH * CinP * KW * CoP;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(i % CoP);
+    long long r = i / CoP;
+    int kx = (int)(r % KW);
+    r /= KW;
+    int ci = (int)(r % CinP);
+    int ky = (int)(r / CinP);
+    Wt[i] = (co < Cout && ci < Cin) ? W[(((long long)co * Cin + ci) * KH + ky) * KW + kx] : 0.f;
+  }
+}
+__global__ void kxexp_unpack_grad_kernel(const float* __restrict__ dWt, float* __restrict__ dW, int Cout, int Cin,
+                                         int KH, int KW, int CinP, int CoP) {
+  long long total = (long long)Cout * Cin * KH * KW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int kx = (int)(i % KW);
+    long long r = i / KW;
+    int ky = (int)(r % KH);
+    r /= KH;
+    int ci = (int)(r % Cin);
+    int co = (int)(r / Cin);
+    dW[i] = dWt[(((long long)ky * CinP + ci) * KW + kx) * CoP + co];
+  }
+}
+// out[p][co] = bias[co] + sum_kx T[(y, x+kx-padW)][kx*CoP+co]
+__global__ void kxexp_reduce_kernel(const float* __restrict__ T, const float* __restrict__ bias,
+                                    float* __restrict__ out, long long P, int W, int KW, int CoP, int padW) {
+  long long total = P * CoP;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(i % CoP);
+    long long pix = i / CoP;
+    int x = (int)(pix % W);
+    float a = bias ? bias[co] : 0.f;
+    for (int kx = 0; kx < KW; ++kx) {
+      int xs = x + kx - padW;
+      if (xs >= 0 && xs < W) a += T[(pix + (kx - padW)) * (long long)(KW * CoP) + kx * CoP + co];
+    }
+    out[i] = a;
+  }
+}
+// dT[(y,x')][kx*CoP+co] = dOut[(y, x' - (kx-padW))][co]  (0 outside the row)
+__global__ void kxexp_expand_kernel(const float* __restrict__ dOut, float* __restrict__ dT, long long P, int W,
+                                    int KW, int CoP, int padW) {
+  const int NC = KW * CoP;
+  long long total = P * NC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % NC);
+    long long pix = i / NC;
+    int kx = c / CoP, co = c - kx * CoP;
+    int x = (int)(pix % W);
+    int xo = x - (kx - padW);
+    dT[i] = (xo >= 0 && xo < W) ? dOut[(pix - (kx - padW)) * CoP + co] : 0.f;
+  }
+}
+
 __global__ void colsum_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ out, long long P,
                               int C, int rows_per_cta) {
   __shared__ float red[4][64];
@@ -525,8 +589,9 @@ int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* 
   p.sA = sA; p.sB = sB; p.sC = sC; p.sBias = sBias;
   p.batch = batch;
   p.flags = flags & (F_ACCUM | F_RELU);
+  p.no_tc = (flags & F_FP32) ? 1 : 0;
   bool split = (flags & F_ATOMIC) != 0;
-  if (flags & 64) {  // F_ZEROC: dense C only
+  if (flags & F_ZEROC) {  // dense C only
     TATT_REQUIRE(ldc == N && (batch == 1 || sC == (long long)M * N), "tatt_gemm: F_ZEROC needs a dense C");
     TATT_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)batch * M * N, (cudaStream_t)stream));
   }
@@ -565,6 +630,45 @@ int tatt_conv_weight_unpack_grad(const float* dWt, float* dW, int Cout, int Cin,
   return 0;
 }
 
+int tatt_conv_kxexp_pack(const float* W, float* Wt, int Cout, int Cin, int KH, int KW, int CinP, int CoP,
+                         void* stream) {
+  long long total = (long long)KH * CinP * KW * CoP;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  kxexp_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, Wt, Cout, Cin, KH, KW, CinP, CoP);
+  TATT_LAUNCH_CHECK("kxexp_pack_kernel");
+  return 0;
+}
+int tatt_conv_kxexp_unpack_grad(const float* dWt, float* dW, int Cout, int Cin, int KH, int KW, int CinP, int CoP,
+                                void* stream) {
+  long long total = (long long)Cout * Cin * KH * KW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  kxexp_unpack_grad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dWt, dW, Cout, Cin, KH, KW, CinP, CoP);
+  TATT_LAUNCH_CHECK("kxexp_unpack_grad_kernel");
+  return 0;
+}
+int tatt_conv_kxexp_reduce(const float* T, const float* bias, float* out, long long P, int W, int KW, int CoP,
+                           int padW, void* stream) {
+  if (P <= 0) return 0;
+  long long total = P * CoP;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  kxexp_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(T, bias, out, P, W, KW, CoP, padW);
+  TATT_LAUNCH_CHECK("kxexp_reduce_kernel");
+  return 0;
+}
+int tatt_conv_kxexp_expand(const float* dOut, float* dT, long long P, int W, int KW, int CoP, int padW,
+                           void* stream) {
+  if (P <= 0) return 0;
+  long long total = P * KW * CoP;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  kxexp_expand_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dOut, dT, P, W, KW, CoP, padW);
+  TATT_LAUNCH_CHECK("kxexp_expand_kernel");
+  return 0;
+}
+
 // Y[nimg*H*W][Cout] (=|+=) im2col(X[nimg][H][W][Cin]) * Wt[KH*KW*Cin][Cout] + bias ; stride 1.
 int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W, int Cin,
                       int Cout, int KH, int KW, int padH, int padW, int flags, void* stream) {
@@ -576,6 +680,7 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
   p.lda = 0; p.ldb = Cout; p.ldc = Cout;
   p.batch = 1;
   p.flags = flags & (F_ACCUM | F_RELU);
+  p.no_tc = (flags & F_FP32) ? 1 : 0;
   p.cH = H; p.cW = W; p.cC = Cin; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
   p.fdHW = make_fd(H * W); p.fdW = make_fd(W); p.fdC = make_fd(Cin); p.fdKW = make_fd(KW);
   return run_gemm(p, A_IM2COL, B_KN, false, (cudaStream_t)stream);
@@ -583,7 +688,7 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
 
 // dWt[KH*KW*Cin][Cout] = im2col(X)^T * dY[nimg*H*W][Cout]   (zeroed here, split-K atomics)
 int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cin, int Cout,
-                      int KH, int KW, int padH, int padW, void* stream) {
+                      int KH, int KW, int padH, int padW, int flags, void* stream) {
   TATT_REQUIRE(Cin % 4 == 0, "conv2d_wgrad: Cin (%d) must be a multiple of 4", Cin);
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv2d_wgrad: too many pixels");
   cudaStream_t st = (cudaStream_t)stream;
@@ -594,6 +699,7 @@ int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int
   p.lda = 0; p.ldb = Cout; p.ldc = Cout;
   p.batch = 1;
   p.flags = 0;
+  p.no_tc = (flags & F_FP32) ? 1 : 0;
   p.cH = H; p.cW = W; p.cC = Cin; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
   p.fdHW = make_fd(H * W); p.fdW = make_fd(W); p.fdC = make_fd(Cin); p.fdKW = make_fd(KW);
   return run_gemm(p, A_IM2COL_T, B_KN, true, st);

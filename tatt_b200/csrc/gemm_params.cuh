@@ -29,7 +29,7 @@ __device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
 
 enum { A_ROW = 0, A_COL = 1, A_IM2COL = 2, A_IM2COL_T = 3 };
 enum { B_KN = 0, B_NK = 1 };
-enum { F_ACCUM = 1, F_RELU = 2, F_ATOMIC = 4, F_VECA = 8, F_VECB = 16, F_VECC = 32 };
+enum { F_ACCUM = 1, F_RELU = 2, F_ATOMIC = 4, F_VECA = 8, F_VECB = 16, F_VECC = 32, F_ZEROC = 64, F_FP32 = 128 };
 
 struct GemmP {
   const float* A;
@@ -41,6 +41,7 @@ struct GemmP {
   long long sA, sB, sC, sBias;
   int batch, splitk, kper;
   int flags;
+  int no_tc;   // 1: force the fp32 FFMA kernels (ill-conditioned sub-graphs, e.g. the STN head)
   // conv geometry (IM2COL modes): X[nimg][cH][cW][cC]
   int cH, cW, cC, KH, KW, padH, padW;
   FastDiv fdHW, fdW, fdC, fdKW;

@@ -480,15 +480,34 @@ static int launch_bn(const GemmP& p, int amode, int bmode, cudaStream_t st) {
 // p.flags carries F_ACCUM / F_RELU / F_VEC* already resolved by the caller (run_gemm in gemm.cu)
 int tatt_tc_gemm_launch(GemmP p, int amode, int bmode, bool want_split, cudaStream_t st) {
   if (p.N <= 4 || p.K < 32 || p.M < 32) return -1;
-  const int BNc = (p.N <= 64) ? 64 : 256;
+  int BNc = (p.N <= 64) ? 64 : 256;
+  // few-tile problems (the RPE recurrent GEMMs: M = 128): prefer narrow N tiles so more SMs get work
+  if (BNc == 256 && (long long)ceil_div(p.M, BM) * ceil_div(p.N, 256) * p.batch < 100) BNc = 64;
   p.splitk = 1;
   p.kper = ((p.K + BK - 1) / BK) * BK;
+  const long long tiles = (long long)ceil_div(p.M, BM) * ceil_div(p.N, BNc) * p.batch;
+  bool split = want_split;
+  int sk = 1;
   if (want_split) {
-    long long tiles = (long long)ceil_div(p.M, BM) * ceil_div(p.N, BNc) * p.batch;
     long long target = 148LL * 2;
-    int sk = (int)((target + tiles - 1) / tiles);
+    sk = (int)((target + tiles - 1) / tiles);
     int maxsk = ceil_div(p.K, BK * 4);
     if (sk > maxsk) sk = maxsk;
+  } else if (tiles < 74 && p.K >= 512 && !(p.flags & F_RELU)) {
+    // automatic split-K: partial sums are atomically added on top of C (zeroed first unless accumulating)
+    sk = (int)((148 + tiles - 1) / tiles);
+    int maxsk = p.K / 256;
+    if (sk > maxsk) sk = maxsk;
+    if (sk > 1) {
+      split = true;
+      if (!(p.flags & F_ACCUM)) {
+        for (int b = 0; b < p.batch; ++b)
+          TATT_CUDA(cudaMemset2DAsync(p.C + (long long)b * p.sC, sizeof(float) * p.ldc, 0, sizeof(float) * p.N,
+                                      (size_t)p.M, st));
+      }
+    }
+  }
+  if (split) {
     if (sk < 1) sk = 1;
     int kper = ceil_div(p.K, sk);
     kper = ((kper + BK - 1) / BK) * BK;

@@ -11,7 +11,23 @@ from . import _cabi
 
 Tensor = torch.Tensor
 ACT_NONE, ACT_RELU, ACT_MISH = 0, 1, 2
-F_ACCUM, F_RELU, F_SPLITK, F_ZEROC = 1, 2, 4, 64
+F_ACCUM, F_RELU, F_SPLITK, F_ZEROC, F_FP32 = 1, 2, 4, 64, 128
+_precision_flag = 0      # OR-ed into every GEMM / conv call; F_FP32 inside `full_fp32()`
+
+
+class full_fp32:
+    """Run the enclosed GEMMs / convolutions on the fp32 FFMA kernels instead of the tcgen05 bf16x3 path
+    (relative error 2^-24 instead of 2^-16).  Used for the STN head, whose BatchNorm1d over a handful of
+    samples amplifies operand rounding by orders of magnitude."""
+
+    def __enter__(self):
+        global _precision_flag
+        self._old = _precision_flag
+        _precision_flag = F_FP32
+
+    def __exit__(self, *a):
+        global _precision_flag
+        _precision_flag = self._old
 
 
 def _stream() -> int:
@@ -45,7 +61,7 @@ def gemm(amode: int, bmode: int, A: Tensor, lda: int, B: Tensor, ldb: int, C: Te
          bias: Optional[Tensor], M: int, N: int, K: int, flags: int = 0, batch: int = 1, sA: int = 0, sB: int = 0,
          sC: int = 0, sBias: int = 0) -> None:
     _cabi.call("tatt_gemm", amode, bmode, _p(A), lda, _p(B), ldb, _p(C), ldc, _p(bias), M, N, K, batch, sA, sB,
-               sC, sBias, flags, _stream())
+               sC, sBias, flags | _precision_flag, _stream())
 
 
 def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], out: Optional[Tensor] = None, accumulate: bool = False,
@@ -113,14 +129,23 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int) -> Tensor:
     n, h, wd, cin_p = x.shape
     co, ci, kh, kw = w.shape
     cout_p = _pad4(co)
-    wt = conv_pack(w, cin_p, cout_p, False)
     if b is not None and cout_p != co:
         bp = torch.zeros(cout_p, dtype=torch.float32, device=x.device)
         bp[:co].copy_(b)
         b = bp
     y = empty(n, h, wd, cout_p, like=x)
-    _cabi.call("tatt_conv2d_igemm", _p(x), _p(wt), _p(b), _p(y), n, h, wd, cin_p, cout_p, kh, kw, pad, pad, 0,
-               _stream())
+    if cout_p == 4 and kw > 1 and cin_p >= 16:
+        # kx-expansion (see gemm.cu): vertical-tap GEMM with N = kw*4, then a horizontal shift-sum
+        wte = empty(kh * cin_p, kw * 4, like=x)
+        _cabi.call("tatt_conv_kxexp_pack", _p(w.contiguous()), _p(wte), co, ci, kh, kw, cin_p, 4, _stream())
+        t = empty(n * h * wd, kw * 4, like=x)
+        _cabi.call("tatt_conv2d_igemm", _p(x), _p(wte), None, _p(t), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0,
+                   _precision_flag, _stream())
+        _cabi.call("tatt_conv_kxexp_reduce", _p(t), _p(b), _p(y), n * h * wd, wd, kw, 4, pad, _stream())
+        return y
+    wt = conv_pack(w, cin_p, cout_p, False)
+    _cabi.call("tatt_conv2d_igemm", _p(x), _p(wt), _p(b), _p(y), n, h, wd, cin_p, cout_p, kh, kw, pad, pad,
+               _precision_flag, _stream())
     return y
 
 
@@ -131,9 +156,20 @@ def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True,
     co, ci, kh, kw = w.shape
     cout_p = dy.shape[-1]
     dx = dw = db = None
-    if need_dw:
+    if need_dw and cout_p == 4 and kw > 1 and cin_p >= 16:
+        dt = empty(n * h * wd, kw * 4, like=x)
+        _cabi.call("tatt_conv_kxexp_expand", _p(dy), _p(dt), n * h * wd, wd, kw, 4, pad, _stream())
+        dwte = empty(kh * cin_p, kw * 4, like=x)
+        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dt), _p(dwte), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0, _precision_flag,
+                   _stream())
+        dw = empty(co, ci, kh, kw, like=x)
+        _cabi.call("tatt_conv_kxexp_unpack_grad", _p(dwte), _p(dw), co, ci, kh, kw, cin_p, 4, _stream())
+        if has_bias:
+            db = colsum(dy.view(-1, cout_p))[:co]
+    elif need_dw:
         dwt = empty(kh * kw * cin_p, cout_p, like=x)
-        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dy), _p(dwt), n, h, wd, cin_p, cout_p, kh, kw, pad, pad, _stream())
+        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dy), _p(dwt), n, h, wd, cin_p, cout_p, kh, kw, pad, pad, _precision_flag,
+                   _stream())
         dw = empty(co, ci, kh, kw, like=x)
         _cabi.call("tatt_conv_weight_unpack_grad", _p(dwt), _p(dw), co, ci, kh, kw, cin_p, cout_p, _stream())
         if has_bias:
@@ -142,7 +178,7 @@ def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True,
         wb = conv_pack(w, cin_p, cout_p, True)
         dx = empty(n, h, wd, cin_p, like=x)
         _cabi.call("tatt_conv2d_igemm", _p(dy), _p(wb), None, _p(dx), n, h, wd, cout_p, cin_p, kh, kw,
-                   kh - 1 - pad, kw - 1 - pad, 0, _stream())
+                   kh - 1 - pad, kw - 1 - pad, _precision_flag, _stream())
     return dx, dw, db
 
 

@@ -54,7 +54,11 @@ class StageFn(torch.autograd.Function):
         for (raw, to_raw), g in zip(ctx.outs_raw, gouts):
             if g is not None:
                 tape.seed(raw, to_raw(g))
-        tape.backward()
+        if getattr(tape, "fp32", False):
+            with ops.full_fp32():
+                tape.backward()
+        else:
+            tape.backward()
         grads = []
         for i, spec in enumerate(ctx.ins):
             g = None
@@ -357,6 +361,11 @@ def stn_tps_stage(stn_head: torch.nn.Module, tps: torch.nn.Module, x: Tensor, tr
     pools = {0: (2, 2), 2: (2, 2), 4: (2, 2), 6: (2, 2), 8: (1, 2)}
 
     def build(tape: Tape, t):
+        tape.fp32 = True                       # backward closures run under the same precision mode
+        with ops.full_fp32():
+            return _build(tape, t)
+
+    def _build(tape: Tape, t):
         xin = ops._chk(t[0].contiguous(), "input image")
         N, Cin, H, W = xin.shape
         x4 = ops.nchw_to_nhwc(xin, 4)

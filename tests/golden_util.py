@@ -14,11 +14,11 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 CASES = {
     # name: (class, ctor kwargs, N, training)
-    "tatt_g16_stn_train_n3": ("TSRN_TL_TRANS", dict(scale_factor=2, width=128, height=32, STN=True, mask=True), 3, True),
+    "tatt_g16_stn_train_n3": ("TSRN_TL_TRANS", dict(scale_factor=2, width=128, height=32, STN=True, mask=True), 6, True),
     "tatt_g16_eval_n2": ("TSRN_TL_TRANS", dict(scale_factor=2, width=128, height=32, STN=True, mask=True), 2, False),
     "tatt_g32_train_n2": ("TSRN_TL_TRANS", dict(scale_factor=2, width=256, height=64, STN=False, mask=True), 2, True),
     "tatt_tiny_rgb_train_n2": ("TSRN_TL_TRANS", dict(scale_factor=2, width=32, height=16, STN=False, mask=False), 2, True),
-    "tsrn_g16_stn_train_n3": ("TSRN", dict(scale_factor=2, width=128, height=32, STN=True, mask=True), 3, True),
+    "tsrn_g16_stn_train_n3": ("TSRN", dict(scale_factor=2, width=128, height=32, STN=True, mask=True), 6, True),
 }
 SEED = 1234
 
