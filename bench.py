@@ -133,6 +133,7 @@ def conv_roofline(dev, batch, h, w, peaks):
     wt = torch.randn(64, 64, 3, 3, device=dev) * 0.05
     b = torch.zeros(64, device=dev)
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)          # 256 MiB > L2
+    ws, wsb = ops._ws(x, x.numel() + 576 * 64)
     for _ in range(3):
         ops.conv2d_fwd(x, wt, b, 1)
     ts = []
@@ -144,7 +145,7 @@ def conv_roofline(dev, batch, h, w, peaks):
         e0.record()
         from tatt_b200 import _cabi
         _cabi.call("tatt_conv2d_igemm", x.data_ptr(), wtp.data_ptr(), b.data_ptr(), y.data_ptr(), batch, h, w, 64, 64,
-                   3, 3, 1, 1, 0, ops._stream())
+                   3, 3, 1, 1, 0, ws.data_ptr(), wsb, ops._stream())
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e-3)

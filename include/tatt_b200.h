@@ -28,10 +28,12 @@ int tatt_arch(void);
  * model/tsrn.py:170,1070 ; model/transformer_v2.py:453-458,785-790,177 ; model/stn_head.py:49-53
  * amode: 0 A[M][K] row-major, 1 A given as [K][M].  bmode: 0 B[K][N], 1 B given as [N][K].
  * flags: 1 accumulate into C, 2 ReLU epilogue, 4 split-K with atomics (C must be zero, or add 64 to
- * have a dense C zeroed here), 128 force the fp32 FFMA kernels instead of the tcgen05 bf16x3 path.  batch > 1 strides A/B/C/bias by sA/sB/sC/sBias elements. */
+ * have a dense C zeroed here), 128 force the fp32 FFMA kernels instead of the tcgen05 bf16x3 path.
+ * ws / ws_bytes: optional device scratch (16-byte aligned, >= 4*(|A|+|B|) bytes rounded up per row to 8
+ * elements) for the pre-split bf16 operand planes of the v2 tcgen05 engine; NULL selects the in-loop split.  batch > 1 strides A/B/C/bias by sA/sB/sC/sBias elements. */
 int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* B, long long ldb, float* C,
               long long ldc, const float* bias, int M, int N, int K, int batch, long long sA, long long sB,
-              long long sC, long long sBias, int flags, void* stream);
+              long long sC, long long sBias, int flags, void* ws, long long ws_bytes, void* stream);
 /* out[c] (+)= sum_r X[r*ldx + c] */
 int tatt_colsum(const float* X, long long ldx, float* out, long long P, int C, int zero_first, void* stream);
 
@@ -44,9 +46,10 @@ int tatt_conv_weight_pack(const float* W, float* Wt, int Cout, int Cin, int KH, 
 int tatt_conv_weight_unpack_grad(const float* dWt, float* dW, int Cout, int Cin, int KH, int KW, int CinP,
                                  int CoutP, void* stream);
 int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W, int Cin,
-                      int Cout, int KH, int KW, int padH, int padW, int flags, void* stream);
+                      int Cout, int KH, int KW, int padH, int padW, int flags, void* ws, long long ws_bytes,
+                      void* stream);
 int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cin, int Cout,
-                      int KH, int KW, int padH, int padW, int flags, void* stream);
+                      int KH, int KW, int padH, int padW, int flags, void* ws, long long ws_bytes, void* stream);
 
 /* 9x9 convolution with <= 4 output channels (tsrn.py:623) as a K = KH*Cin, N = KW*CoP GEMM over the vertical
  * taps (tatt_conv2d_igemm / tatt_conv2d_wgrad with KW=1) plus these horizontal shift-sum / shift-expand passes */

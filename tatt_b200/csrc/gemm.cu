@@ -402,6 +402,14 @@ static int run_gemm(GemmP p, int amode, int bmode, bool want_split, cudaStream_t
     const char* e = getenv("TATT_TC");
     return !(e && e[0] == '0');
   }();
+  static const bool tc2_on = []() {
+    const char* e = getenv("TATT_TC2");
+    return !(e && e[0] == '0');
+  }();
+  if (tc_on && tc2_on && !p.no_tc && p.ws) {
+    int rc = tatt_tc2_gemm_launch(p, amode, bmode, want_split, p.ws, p.ws_bytes, st);
+    if (rc >= 0) return rc;
+  }
   if (tc_on && !p.no_tc) {
     int rc = tatt_tc_gemm_launch(p, amode, bmode, want_split, st);
     if (rc >= 0) return rc;
@@ -578,7 +586,7 @@ extern "C" {
 
 int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* B, long long ldb, float* C,
               long long ldc, const float* bias, int M, int N, int K, int batch, long long sA, long long sB,
-              long long sC, long long sBias, int flags, void* stream) {
+              long long sC, long long sBias, int flags, void* ws, long long ws_bytes, void* stream) {
   TATT_REQUIRE(amode == A_ROW || amode == A_COL, "tatt_gemm: amode must be 0 (row) or 1 (col)");
   TATT_REQUIRE(bmode == B_KN || bmode == B_NK, "tatt_gemm: bad bmode");
   TATT_REQUIRE(batch >= 1 && M >= 0 && N >= 0 && K >= 0, "tatt_gemm: bad sizes");
@@ -590,6 +598,8 @@ int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* 
   p.batch = batch;
   p.flags = flags & (F_ACCUM | F_RELU);
   p.no_tc = (flags & F_FP32) ? 1 : 0;
+  p.ws = ws;
+  p.ws_bytes = ws_bytes;
   bool split = (flags & F_ATOMIC) != 0;
   if (flags & F_ZEROC) {  // dense C only
     TATT_REQUIRE(ldc == N && (batch == 1 || sC == (long long)M * N), "tatt_gemm: F_ZEROC needs a dense C");
@@ -671,7 +681,8 @@ int tatt_conv_kxexp_expand(const float* dOut, float* dT, long long P, int W, int
 
 // Y[nimg*H*W][Cout] (=|+=) im2col(X[nimg][H][W][Cin]) * Wt[KH*KW*Cin][Cout] + bias ; stride 1.
 int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W, int Cin,
-                      int Cout, int KH, int KW, int padH, int padW, int flags, void* stream) {
+                      int Cout, int KH, int KW, int padH, int padW, int flags, void* ws, long long ws_bytes,
+                      void* stream) {
   TATT_REQUIRE(Cin % 4 == 0, "conv2d_igemm: Cin (%d) must be a multiple of 4 (pad channels)", Cin);
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv2d_igemm: too many pixels");
   GemmP p = {};
@@ -681,6 +692,8 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
   p.batch = 1;
   p.flags = flags & (F_ACCUM | F_RELU);
   p.no_tc = (flags & F_FP32) ? 1 : 0;
+  p.ws = ws;
+  p.ws_bytes = ws_bytes;
   p.cH = H; p.cW = W; p.cC = Cin; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
   p.fdHW = make_fd(H * W); p.fdW = make_fd(W); p.fdC = make_fd(Cin); p.fdKW = make_fd(KW);
   return run_gemm(p, A_IM2COL, B_KN, false, (cudaStream_t)stream);
@@ -688,7 +701,7 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
 
 // dWt[KH*KW*Cin][Cout] = im2col(X)^T * dY[nimg*H*W][Cout]   (zeroed here, split-K atomics)
 int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cin, int Cout,
-                      int KH, int KW, int padH, int padW, int flags, void* stream) {
+                      int KH, int KW, int padH, int padW, int flags, void* ws, long long ws_bytes, void* stream) {
   TATT_REQUIRE(Cin % 4 == 0, "conv2d_wgrad: Cin (%d) must be a multiple of 4", Cin);
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv2d_wgrad: too many pixels");
   cudaStream_t st = (cudaStream_t)stream;
@@ -700,6 +713,8 @@ int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int
   p.batch = 1;
   p.flags = 0;
   p.no_tc = (flags & F_FP32) ? 1 : 0;
+  p.ws = ws;
+  p.ws_bytes = ws_bytes;
   p.cH = H; p.cW = W; p.cC = Cin; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
   p.fdHW = make_fd(H * W); p.fdW = make_fd(W); p.fdC = make_fd(Cin); p.fdKW = make_fd(KW);
   return run_gemm(p, A_IM2COL_T, B_KN, true, st);

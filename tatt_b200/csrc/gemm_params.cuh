@@ -41,6 +41,8 @@ struct GemmP {
   long long sA, sB, sC, sBias;
   int batch, splitk, kper;
   int flags;
+  void* ws;            // optional workspace for the pre-split bf16 planes of the v2 tcgen05 engine
+  long long ws_bytes;
   int no_tc;   // 1: force the fp32 FFMA kernels (ill-conditioned sub-graphs, e.g. the STN head)
   // conv geometry (IM2COL modes): X[nimg][cH][cW][cC]
   int cH, cW, cC, KH, KW, padH, padW;
@@ -50,3 +52,6 @@ struct GemmP {
 
 // tcgen05 path (tc_gemm.cu); returns 0 on success, -1 if the shape is not eligible (caller falls through to FFMA)
 int tatt_tc_gemm_launch(GemmP p, int amode, int bmode, bool want_split, cudaStream_t st);
+// v2 (tc2_gemm.cu): operands pre-split into bf16 planes in `ws`; same return convention
+int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* ws, long long ws_bytes,
+                         cudaStream_t st);

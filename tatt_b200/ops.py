@@ -52,6 +52,18 @@ def _rows(t: Tensor) -> Tuple[int, int, int]:
     return t.shape[0], t.shape[1], (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
 
 
+def _r8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _ws(like: Tensor, nelems: int):
+    """Scratch for the bf16 hi/lo operand planes (2 planes x 2 bytes per element), or (None, 0)."""
+    if _precision_flag & F_FP32:
+        return None, 0
+    nbytes = 4 * nelems + 1024
+    return torch.empty(nbytes, dtype=torch.uint8, device=like.device), nbytes
+
+
 def empty(*shape, like: Tensor) -> Tensor:
     return torch.empty(*shape, dtype=torch.float32, device=like.device)
 
@@ -60,8 +72,11 @@ def empty(*shape, like: Tensor) -> Tensor:
 def gemm(amode: int, bmode: int, A: Tensor, lda: int, B: Tensor, ldb: int, C: Tensor, ldc: int,
          bias: Optional[Tensor], M: int, N: int, K: int, flags: int = 0, batch: int = 1, sA: int = 0, sB: int = 0,
          sC: int = 0, sBias: int = 0) -> None:
+    ws, wsb = (None, 0)
+    if M >= 32 and K >= 32 and N > 4:
+        ws, wsb = _ws(C, batch * (_r8(M) * _r8(K) + _r8(N) * _r8(K)))
     _cabi.call("tatt_gemm", amode, bmode, _p(A), lda, _p(B), ldb, _p(C), ldc, _p(bias), M, N, K, batch, sA, sB,
-               sC, sBias, flags | _precision_flag, _stream())
+               sC, sBias, flags | _precision_flag, _p(ws), wsb, _stream())
 
 
 def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], out: Optional[Tensor] = None, accumulate: bool = False,
@@ -139,13 +154,15 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int) -> Tensor:
         wte = empty(kh * cin_p, kw * 4, like=x)
         _cabi.call("tatt_conv_kxexp_pack", _p(w.contiguous()), _p(wte), co, ci, kh, kw, cin_p, 4, _stream())
         t = empty(n * h * wd, kw * 4, like=x)
+        ws, wsb = _ws(x, x.numel() + kh * cin_p * _r8(kw * 4))
         _cabi.call("tatt_conv2d_igemm", _p(x), _p(wte), None, _p(t), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0,
-                   _precision_flag, _stream())
+                   _precision_flag, _p(ws), wsb, _stream())
         _cabi.call("tatt_conv_kxexp_reduce", _p(t), _p(b), _p(y), n * h * wd, wd, kw, 4, pad, _stream())
         return y
     wt = conv_pack(w, cin_p, cout_p, False)
+    ws, wsb = _ws(x, x.numel() + kh * kw * cin_p * _r8(cout_p))
     _cabi.call("tatt_conv2d_igemm", _p(x), _p(wt), _p(b), _p(y), n, h, wd, cin_p, cout_p, kh, kw, pad, pad,
-               _precision_flag, _stream())
+               _precision_flag, _p(ws), wsb, _stream())
     return y
 
 
@@ -160,16 +177,18 @@ def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True,
         dt = empty(n * h * wd, kw * 4, like=x)
         _cabi.call("tatt_conv_kxexp_expand", _p(dy), _p(dt), n * h * wd, wd, kw, 4, pad, _stream())
         dwte = empty(kh * cin_p, kw * 4, like=x)
+        ws, wsb = _ws(x, x.numel() + n * h * wd * _r8(kw * 4))
         _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dt), _p(dwte), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0, _precision_flag,
-                   _stream())
+                   _p(ws), wsb, _stream())
         dw = empty(co, ci, kh, kw, like=x)
         _cabi.call("tatt_conv_kxexp_unpack_grad", _p(dwte), _p(dw), co, ci, kh, kw, cin_p, 4, _stream())
         if has_bias:
             db = colsum(dy.view(-1, cout_p))[:co]
     elif need_dw:
         dwt = empty(kh * kw * cin_p, cout_p, like=x)
+        ws, wsb = _ws(x, x.numel() + n * h * wd * _r8(cout_p))
         _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dy), _p(dwt), n, h, wd, cin_p, cout_p, kh, kw, pad, pad, _precision_flag,
-                   _stream())
+                   _p(ws), wsb, _stream())
         dw = empty(co, ci, kh, kw, like=x)
         _cabi.call("tatt_conv_weight_unpack_grad", _p(dwt), _p(dw), co, ci, kh, kw, cin_p, cout_p, _stream())
         if has_bias:
@@ -177,8 +196,9 @@ def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True,
     if need_dx:
         wb = conv_pack(w, cin_p, cout_p, True)
         dx = empty(n, h, wd, cin_p, like=x)
+        ws, wsb = _ws(x, dy.numel() + kh * kw * cout_p * _r8(cin_p))
         _cabi.call("tatt_conv2d_igemm", _p(dy), _p(wb), None, _p(dx), n, h, wd, cout_p, cin_p, kh, kw,
-                   kh - 1 - pad, kw - 1 - pad, _precision_flag, _stream())
+                   kh - 1 - pad, kw - 1 - pad, _precision_flag, _p(ws), wsb, _stream())
     return dx, dw, db
 
 
