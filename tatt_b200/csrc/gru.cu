@@ -38,43 +38,64 @@ gru32_scan_fwd_kernel(const float* __restrict__ GI, const float* __restrict__ Wh
   float h = 0.f;
   long long row = base + (dir == 0 ? 0 : (long long)(T - 1)) * t_stride;
   const long long step_stride = dir == 0 ? t_stride : -t_stride;
-  const float* gp = GI + row * 192 + dir * 96 + lane;
-  float gr = gp[0], gz = gp[32], gn = gp[64];
-  for (int s = 0; s < T; ++s) {
-    // prefetch the next step's input projections
-    float ngr = 0.f, ngz = 0.f, ngn = 0.f;
-    if (s + 1 < T) {
-      const float* np = GI + (row + step_stride) * 192 + dir * 96 + lane;
-      ngr = np[0];
-      ngz = np[32];
-      ngn = np[64];
-    }
-    float ar = br, az = bz, an = bn;
+  // The recurrence is a dependent chain of ~500 cycles per step while the GI row of a step comes from
+  // L2/HBM (~1000+ cycles): keep a ring of PF steps of input projections in flight.
+  constexpr int PF = 6;
+  float pr[PF], pz[PF], pn[PF];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      float hk = __shfl_sync(0xffffffffu, h, k);
-      ar = fmaf(wr[k], hk, ar);
-      az = fmaf(wz[k], hk, az);
-      an = fmaf(wn[k], hk, an);
+  for (int j = 0; j < PF; ++j) {
+    pr[j] = pz[j] = pn[j] = 0.f;
+    if (j < T) {
+      const float* gp = GI + (row + j * step_stride) * 192 + dir * 96 + lane;
+      pr[j] = gp[0];
+      pz[j] = gp[32];
+      pn[j] = gp[64];
     }
-    float r = sigmoid_f(gr + ar);
-    float z = sigmoid_f(gz + az);
-    float n = tanhf(gn + r * an);
-    float hn = n + z * (h - n);
-    OUT[row * 64 + dir * 32 + lane] = hn;
-    if (GATES) {
-      float* g = GATES + row * 320 + dir * 160 + lane;
-      g[0] = r;
-      g[32] = z;
-      g[64] = n;
-      g[96] = an;
-      g[128] = h;
+  }
+  for (int s0 = 0; s0 < T; s0 += PF) {
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int s = s0 + j;
+      if (s < T) {
+        const float gr = pr[j], gz = pz[j], gn = pn[j];
+        if (s + PF < T) {
+          const float* np = GI + (row + PF * step_stride) * 192 + dir * 96 + lane;
+          pr[j] = np[0];
+          pz[j] = np[32];
+          pn[j] = np[64];
+        }
+        float ar = br, az = bz, an = bn;
+        float ar2 = 0.f, az2 = 0.f, an2 = 0.f;          // two partial chains halve the FMA dependency depth
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          float h0 = __shfl_sync(0xffffffffu, h, k), h1 = __shfl_sync(0xffffffffu, h, k + 1);
+          ar = fmaf(wr[k], h0, ar);
+          az = fmaf(wz[k], h0, az);
+          an = fmaf(wn[k], h0, an);
+          ar2 = fmaf(wr[k + 1], h1, ar2);
+          az2 = fmaf(wz[k + 1], h1, az2);
+          an2 = fmaf(wn[k + 1], h1, an2);
+        }
+        ar += ar2;
+        az += az2;
+        an += an2;
+        float r = sigmoid_f(gr + ar);
+        float z = sigmoid_f(gz + az);
+        float n = tanhf(gn + r * an);
+        float hn = n + z * (h - n);
+        OUT[row * 64 + dir * 32 + lane] = hn;
+        if (GATES) {
+          float* g = GATES + row * 320 + dir * 160 + lane;
+          g[0] = r;
+          g[32] = z;
+          g[64] = n;
+          g[96] = an;
+          g[128] = h;
+        }
+        h = hn;
+        row += step_stride;
+      }
     }
-    h = hn;
-    row += step_stride;
-    gr = ngr;
-    gz = ngz;
-    gn = ngn;
   }
 }
 
@@ -99,33 +120,56 @@ gru32_scan_bwd_kernel(const float* __restrict__ dOUT, const float* __restrict__ 
   // walk the recurrence backwards: last processed step first
   long long row = base + (dir == 0 ? (long long)(T - 1) : 0) * t_stride;
   const long long step_stride = dir == 0 ? -t_stride : t_stride;
-  for (int s = 0; s < T; ++s) {
-    const float* g = GATES + row * 320 + dir * 160 + lane;
-    float r = g[0], z = g[32], n = g[64], ghn = g[96], hp = g[128];
-    float go = dOUT[row * 64 + dir * 32 + lane] + dh;
-    float dn = go * (1.f - z);
-    float dz = go * (hp - n);
-    float dpn = dn * (1.f - n * n);
-    float dpr = dpn * ghn * r * (1.f - r);
-    float dpz = dz * z * (1.f - z);
-    float dhn = dpn * r;
-    float* o = dGI + row * 192 + dir * 96 + lane;
-    o[0] = dpr;
-    o[32] = dpz;
-    o[64] = dpn;
-    float* o2 = dGH + row * 192 + dir * 96 + lane;
-    o2[0] = dpr;
-    o2[32] = dpz;
-    o2[64] = dhn;
-    float acc = go * z;
+  constexpr int PF = 4;
+  float qr[PF], qz[PF], qn[PF], qg[PF], qh[PF], qo[PF];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      acc = fmaf(wc[k], __shfl_sync(0xffffffffu, dpr, k), acc);
-      acc = fmaf(wc[32 + k], __shfl_sync(0xffffffffu, dpz, k), acc);
-      acc = fmaf(wc[64 + k], __shfl_sync(0xffffffffu, dhn, k), acc);
+  for (int j = 0; j < PF; ++j) {
+    qr[j] = qz[j] = qn[j] = qg[j] = qh[j] = qo[j] = 0.f;
+    if (j < T) {
+      const long long rj = row + j * step_stride;
+      const float* g = GATES + rj * 320 + dir * 160 + lane;
+      qr[j] = g[0]; qz[j] = g[32]; qn[j] = g[64]; qg[j] = g[96]; qh[j] = g[128];
+      qo[j] = dOUT[rj * 64 + dir * 32 + lane];
     }
-    dh = acc;
-    row += step_stride;
+  }
+  for (int s0 = 0; s0 < T; s0 += PF) {
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int s = s0 + j;
+      if (s < T) {
+        const float r = qr[j], z = qz[j], n = qn[j], ghn = qg[j], hp = qh[j];
+        const float go = qo[j] + dh;
+        if (s + PF < T) {
+          const long long rj = row + PF * step_stride;
+          const float* g = GATES + rj * 320 + dir * 160 + lane;
+          qr[j] = g[0]; qz[j] = g[32]; qn[j] = g[64]; qg[j] = g[96]; qh[j] = g[128];
+          qo[j] = dOUT[rj * 64 + dir * 32 + lane];
+        }
+        float dn = go * (1.f - z);
+        float dz = go * (hp - n);
+        float dpn = dn * (1.f - n * n);
+        float dpr = dpn * ghn * r * (1.f - r);
+        float dpz = dz * z * (1.f - z);
+        float dhn = dpn * r;
+        float* o = dGI + row * 192 + dir * 96 + lane;
+        o[0] = dpr;
+        o[32] = dpz;
+        o[64] = dpn;
+        float* o2 = dGH + row * 192 + dir * 96 + lane;
+        o2[0] = dpr;
+        o2[32] = dpz;
+        o2[64] = dhn;
+        float acc = go * z, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          acc = fmaf(wc[k], __shfl_sync(0xffffffffu, dpr, k), acc);
+          acc2 = fmaf(wc[32 + k], __shfl_sync(0xffffffffu, dpz, k), acc2);
+          acc3 = fmaf(wc[64 + k], __shfl_sync(0xffffffffu, dhn, k), acc3);
+        }
+        dh = acc + acc2 + acc3;
+        row += step_stride;
+      }
+    }
   }
 }
 

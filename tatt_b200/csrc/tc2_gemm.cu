@@ -11,6 +11,7 @@
 //     the pixel/row axis: a shared-memory row is simply one pixel's 64 channels (128 B), no transposition.
 // Three MMAs per k-step (lo*hi + hi*lo + hi*hi) accumulate in fp32 in TMEM, as in v1.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_params.cuh"
 
@@ -447,15 +448,24 @@ static int split_transpose(const float* src, long long ld, int K, int N, int Kp,
   return 0;
 }
 
-template <int KIND>
-static int launch_kind(const Tc2P& q, cudaStream_t st) {
-  constexpr int STAGES = 2;
+template <int KIND, int STAGES>
+static int launch_kind_s(const Tc2P& q, cudaStream_t st) {
   const int smem = STAGES * STAGE_BYTES + 1024;
   dim3 grid(ceil_div(q.M, BM), ceil_div(q.N, BN), q.batch * q.splitk);
   TATT_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<KIND, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   tc2_gemm_kernel<KIND, STAGES><<<grid, NT, smem, st>>>(q);
   TATT_LAUNCH_CHECK("tc2_gemm_kernel");
   return 0;
+}
+template <int KIND>
+static int launch_kind(const Tc2P& q, cudaStream_t st) {
+  // pipeline depth: 2 stages x 2 CTAs/SM (default) or 4 stages x 1 CTA/SM (TATT_TC2_STAGES=4)
+  static const int stages = []() {
+    const char* e = getenv("TATT_TC2_STAGES");
+    return (e && e[0] == '4') ? 4 : 2;
+  }();
+  if (stages == 4) return launch_kind_s<KIND, 4>(q, st);
+  return launch_kind_s<KIND, 2>(q, st);
 }
 
 }  // namespace
