@@ -33,7 +33,14 @@ int tatt_arch(void);
  * elements) for the pre-split bf16 operand planes of the v2 tcgen05 engine; NULL selects the in-loop split.  batch > 1 strides A/B/C/bias by sA/sB/sC/sBias elements. */
 int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* B, long long ldb, float* C,
               long long ldc, const float* bias, int M, int N, int K, int batch, long long sA, long long sB,
-              long long sC, long long sBias, int flags, void* ws, long long ws_bytes, void* stream);
+              long long sC, long long sBias, int flags, long long loA, long long loB, void* ws, long long ws_bytes,
+              void* stream);
+/* Pre-split bf16 hi/lo operand planes (for operands reused by many GEMMs, e.g. W_hh over the RPE recurrence):
+ * planes[rows][round8(cols)], or with transpose=1 planes[cols][round8(rows)].  Pass them to tatt_gemm with
+ * flags 256 (A is the hi plane, lo plane at A + loA bf16 elements, lda/sA in plane elements) / 512 (same for B);
+ * requires amode 0, bmode 1. */
+int tatt_split_bf16(const float* src, long long ld, long long rows, int cols, int transpose, void* hi, void* lo,
+                    void* stream);
 /* out[c] (+)= sum_r X[r*ldx + c] */
 int tatt_colsum(const float* X, long long ldx, float* out, long long P, int C, int zero_first, void* stream);
 
@@ -94,10 +101,13 @@ int tatt_gru32_scan_bwd(const float* dOUT, const float* GATES, const float* Whh,
 /* ---- recurrent positional encoding (batch-axis BiGRU, quirk Q1): model/transformer_v2.py:177,215-221 -- */
 int tatt_rpe_gather(const float* emb, float* X, int H, int W, int C, void* stream);
 int tatt_rpe_scatter(const float* dX, float* demb, int H, int W, int C, void* stream);
-int tatt_rpe_gate_fwd(const float* GI, const float* GH, float* HALL, float* GATES, float* QPOS, int step, int N,
-                      int Wd, int Hd, int C, int Himg, void* stream);
+/* HPL / DGHPL: optional bf16 planes {hi, lo at +plane_lo elements} mirroring HALL / DGH (operands of the next
+ * recurrent GEMM), or NULL */
+int tatt_rpe_gate_fwd(const float* GI, const float* GH, float* HALL, float* GATES, float* QPOS, void* HPL,
+                      long long plane_lo, int step, int N, int Wd, int Hd, int C, int Himg, void* stream);
 int tatt_rpe_gate_bwd(const float* dQPOS, const float* HALL, const float* GATES, float* DH, float* DGISUM,
-                      float* DGH, int step, int N, int Wd, int Hd, int C, int Himg, void* stream);
+                      float* DGH, void* DGHPL, long long plane_lo, int step, int N, int Wd, int Hd, int C, int Himg,
+                      void* stream);
 
 /* ---- multi-head attention core (64 = 4 x 16, <= 32 keys): nn.MultiheadAttention as used at
  * model/transformer_v2.py:476-478 (encoder) and 820-823 (decoder cross-attention) ----------------------- */

@@ -384,7 +384,7 @@ static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0;
 static int run_gemm(GemmP p, int amode, int bmode, bool want_split, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return 0;
   // vector-access eligibility
-  int fl = p.flags & (F_ACCUM | F_RELU);
+  int fl = p.flags & (F_ACCUM | F_RELU | F_APLANES | F_BPLANES);
   bool va, vb;
   if (amode == A_ROW || amode == A_COL)
     va = (p.lda % 4 == 0) && aligned16(p.A) && (p.sA % 4 == 0);
@@ -406,7 +406,7 @@ static int run_gemm(GemmP p, int amode, int bmode, bool want_split, cudaStream_t
     const char* e = getenv("TATT_TC2");
     return !(e && e[0] == '0');
   }();
-  if (tc_on && tc2_on && !p.no_tc && p.ws) {
+  if (tc_on && tc2_on && !p.no_tc && (p.ws || (p.flags & (F_APLANES | F_BPLANES)))) {
     int rc = tatt_tc2_gemm_launch(p, amode, bmode, want_split, p.ws, p.ws_bytes, st);
     if (rc >= 0) return rc;
   }
@@ -586,7 +586,8 @@ extern "C" {
 
 int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* B, long long ldb, float* C,
               long long ldc, const float* bias, int M, int N, int K, int batch, long long sA, long long sB,
-              long long sC, long long sBias, int flags, void* ws, long long ws_bytes, void* stream) {
+              long long sC, long long sBias, int flags, long long loA, long long loB, void* ws, long long ws_bytes,
+              void* stream) {
   TATT_REQUIRE(amode == A_ROW || amode == A_COL, "tatt_gemm: amode must be 0 (row) or 1 (col)");
   TATT_REQUIRE(bmode == B_KN || bmode == B_NK, "tatt_gemm: bad bmode");
   TATT_REQUIRE(batch >= 1 && M >= 0 && N >= 0 && K >= 0, "tatt_gemm: bad sizes");
@@ -596,16 +597,30 @@ int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* 
   p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.sA = sA; p.sB = sB; p.sC = sC; p.sBias = sBias;
   p.batch = batch;
-  p.flags = flags & (F_ACCUM | F_RELU);
+  p.flags = flags & (F_ACCUM | F_RELU | F_APLANES | F_BPLANES);
+  p.loA = loA;
+  p.loB = loB;
   p.no_tc = (flags & F_FP32) ? 1 : 0;
   p.ws = ws;
   p.ws_bytes = ws_bytes;
+  if (flags & (F_APLANES | F_BPLANES)) {
+    int rc = tatt_tc2_gemm_launch(p, amode, bmode, false, ws, ws_bytes, (cudaStream_t)stream);
+    if (rc < 0) return tatt_set_error("tatt_gemm: operand planes need the tcgen05 path");
+    return rc;
+  }
   bool split = (flags & F_ATOMIC) != 0;
   if (flags & F_ZEROC) {  // dense C only
     TATT_REQUIRE(ldc == N && (batch == 1 || sC == (long long)M * N), "tatt_gemm: F_ZEROC needs a dense C");
     TATT_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)batch * M * N, (cudaStream_t)stream));
   }
   return run_gemm(p, amode, bmode, split, (cudaStream_t)stream);
+}
+
+// bf16 hi/lo operand planes for tatt_gemm flags 256 (A) / 512 (B): planes[rows][round8(cols)] or, transposed,
+// planes[cols][round8(rows)]
+int tatt_split_bf16(const float* src, long long ld, long long rows, int cols, int transpose, void* hi, void* lo,
+                    void* stream) {
+  return tatt_tc2_split(src, ld, rows, cols, transpose, hi, lo, (cudaStream_t)stream);
 }
 
 int tatt_colsum(const float* X, long long ldx, float* out, long long P, int C, int zero_first, void* stream) {

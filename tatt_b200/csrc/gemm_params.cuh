@@ -29,7 +29,7 @@ __device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
 
 enum { A_ROW = 0, A_COL = 1, A_IM2COL = 2, A_IM2COL_T = 3 };
 enum { B_KN = 0, B_NK = 1 };
-enum { F_ACCUM = 1, F_RELU = 2, F_ATOMIC = 4, F_VECA = 8, F_VECB = 16, F_VECC = 32, F_ZEROC = 64, F_FP32 = 128 };
+enum { F_ACCUM = 1, F_RELU = 2, F_ATOMIC = 4, F_VECA = 8, F_VECB = 16, F_VECC = 32, F_ZEROC = 64, F_FP32 = 128, F_APLANES = 256, F_BPLANES = 512 };
 
 struct GemmP {
   const float* A;
@@ -41,6 +41,7 @@ struct GemmP {
   long long sA, sB, sC, sBias;
   int batch, splitk, kper;
   int flags;
+  long long loA, loB;  // F_APLANES / F_BPLANES: element offset from the hi plane (A / B pointer) to the lo plane
   void* ws;            // optional workspace for the pre-split bf16 planes of the v2 tcgen05 engine
   long long ws_bytes;
   int no_tc;   // 1: force the fp32 FFMA kernels (ill-conditioned sub-graphs, e.g. the STN head)
@@ -52,6 +53,8 @@ struct GemmP {
 
 // tcgen05 path (tc_gemm.cu); returns 0 on success, -1 if the shape is not eligible (caller falls through to FFMA)
 int tatt_tc_gemm_launch(GemmP p, int amode, int bmode, bool want_split, cudaStream_t st);
+int tatt_tc2_split(const float* src, long long ld, long long rows, int cols, int transpose, void* hi, void* lo,
+                   cudaStream_t st);
 // v2 (tc2_gemm.cu): operands pre-split into bf16 planes in `ws`; same return convention
 int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* ws, long long ws_bytes,
                          cudaStream_t st);

@@ -6,9 +6,16 @@
 //  (2) RPE BiGRU of the TP Interpreter (model/transformer_v2.py:177, 215-221; quirk Q1: recurrence
 //      over the BATCH axis): per-step gate kernels around the batched recurrent GEMM (gemm.cu).
 // Gate order r,z,n; n = tanh(gi_n + r * (W_hn h + b_hn)); h' = (1-z) n + z h   (torch.nn.GRU).
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16* hi, __nv_bfloat16* lo, long long i) {
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
 
 // GI    [rows][192]  = [dir][gate][32]   (x W_ih^T + b_ih, both directions)
 // OUT   [rows][64]   = [dir][32]
@@ -205,7 +212,8 @@ __global__ void rpe_scatter_kernel(const float* __restrict__ dX, float* __restri
 //  GATES[N][2][Wd][4][Hd]  r,z,n,ghn (saved)       QPOS [N][Himg*Wd][C]
 __global__ void rpe_gate_fwd_kernel(const float* __restrict__ GI, const float* __restrict__ GH,
                                     float* __restrict__ HALL, float* __restrict__ GATES,
-                                    float* __restrict__ QPOS, int step, int N, int Wd, int Hd, int C, int Himg) {
+                                    float* __restrict__ QPOS, __nv_bfloat16* __restrict__ HPL, long long plane_lo,
+                                    int step, int N, int Wd, int Hd, int C, int Himg) {
   long long n = 2LL * Wd * Hd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -223,6 +231,7 @@ __global__ void rpe_gate_fwd_kernel(const float* __restrict__ GI, const float* _
     float hp = HALL[hidx];
     float hn = nn + zz * (hp - nn);
     HALL[hidx + (long long)Wd * Hd] = hn;
+    if (HPL) split_bf16(hn, HPL, HPL + plane_lo, hidx + (long long)Wd * Hd);
     if (GATES) {
       long long gi = ((((long long)step * 2 + dir) * Wd + w) * 4) * Hd + j;
       GATES[gi] = rr;
@@ -243,7 +252,8 @@ __global__ void rpe_gate_fwd_kernel(const float* __restrict__ GI, const float* _
 //  DGH   [2][N][Wd][3Hd] per-step grad wrt (W_hh h + b_hh)
 __global__ void rpe_gate_bwd_kernel(const float* __restrict__ dQPOS, const float* __restrict__ HALL,
                                     const float* __restrict__ GATES, float* __restrict__ DH,
-                                    float* __restrict__ DGISUM, float* __restrict__ DGH, int step, int N, int Wd,
+                                    float* __restrict__ DGISUM, float* __restrict__ DGH,
+                                    __nv_bfloat16* __restrict__ DGHPL, long long plane_lo, int step, int N, int Wd,
                                     int Hd, int C, int Himg) {
   long long n = 2LL * Wd * Hd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -272,6 +282,11 @@ __global__ void rpe_gate_bwd_kernel(const float* __restrict__ dQPOS, const float
     DGH[d3] = dpr;
     DGH[d3 + Hd] = dpz;
     DGH[d3 + 2 * Hd] = dpn * rr;
+    if (DGHPL) {
+      split_bf16(dpr, DGHPL, DGHPL + plane_lo, d3);
+      split_bf16(dpz, DGHPL, DGHPL + plane_lo, d3 + Hd);
+      split_bf16(dpn * rr, DGHPL, DGHPL + plane_lo, d3 + 2 * Hd);
+    }
     DH[i] = go * zz;
   }
 }
@@ -320,20 +335,23 @@ int tatt_rpe_scatter(const float* dX, float* demb, int H, int W, int C, void* st
   return 0;
 }
 
-int tatt_rpe_gate_fwd(const float* GI, const float* GH, float* HALL, float* GATES, float* QPOS, int step, int N,
-                      int Wd, int Hd, int C, int Himg, void* stream) {
+int tatt_rpe_gate_fwd(const float* GI, const float* GH, float* HALL, float* GATES, float* QPOS, void* HPL,
+                      long long plane_lo, int step, int N, int Wd, int Hd, int C, int Himg, void* stream) {
   TATT_REQUIRE(2 * Hd == Himg * C, "rpe_gate_fwd: 2*Hd (%d) must equal Himg*C (%d)", 2 * Hd, Himg * C);
   long long n = 2LL * Wd * Hd;
-  rpe_gate_fwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(GI, GH, HALL, GATES, QPOS, step, N,
+  rpe_gate_fwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(GI, GH, HALL, GATES, QPOS,
+                                                                                (__nv_bfloat16*)HPL, plane_lo, step, N,
                                                                                 Wd, Hd, C, Himg);
   TATT_LAUNCH_CHECK("rpe_gate_fwd_kernel");
   return 0;
 }
 int tatt_rpe_gate_bwd(const float* dQPOS, const float* HALL, const float* GATES, float* DH, float* DGISUM,
-                      float* DGH, int step, int N, int Wd, int Hd, int C, int Himg, void* stream) {
+                      float* DGH, void* DGHPL, long long plane_lo, int step, int N, int Wd, int Hd, int C, int Himg,
+                      void* stream) {
   TATT_REQUIRE(2 * Hd == Himg * C, "rpe_gate_bwd: 2*Hd (%d) must equal Himg*C (%d)", 2 * Hd, Himg * C);
   long long n = 2LL * Wd * Hd;
   rpe_gate_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dQPOS, HALL, GATES, DH, DGISUM, DGH,
+                                                                                (__nv_bfloat16*)DGHPL, plane_lo,
                                                                                 step, N, Wd, Hd, C, Himg);
   TATT_LAUNCH_CHECK("rpe_gate_bwd_kernel");
   return 0;

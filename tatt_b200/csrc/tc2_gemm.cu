@@ -470,10 +470,24 @@ static int launch_kind(const Tc2P& q, cudaStream_t st) {
 
 }  // namespace
 
+// planes [rows][rup8(cols)] (transpose == 0) or [cols][rup8(rows)] (transpose == 1), zero padded
+int tatt_tc2_split(const float* src, long long ld, long long rows, int cols, int transpose, void* hi, void* lo,
+                   cudaStream_t st) {
+  if (!transpose)
+    return split_dense(src, ld, rows, cols, (int)rup8(cols), (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, st);
+  return split_transpose(src, ld, (int)rows, cols, (int)rup8(rows), (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, st);
+}
+
 // Returns 0 on success, 1 on error, -1 when the shape is not eligible or the workspace is too small
 int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* ws, long long ws_bytes,
                          cudaStream_t st) {
-  if (ws == nullptr || p.N <= 4 || p.K < 32 || p.M < 32) return -1;
+  const bool a_pl = (p.flags & F_APLANES) != 0, b_pl = (p.flags & F_BPLANES) != 0;
+  if ((ws == nullptr && !(a_pl && b_pl)) || p.N <= 4 || p.K < 32 || p.M < 32) {
+    if (a_pl || b_pl) return tatt_set_error("tc2_gemm: pre-split operand planes given for an ineligible shape");
+    return -1;
+  }
+  if ((a_pl || b_pl) && (amode != A_ROW || bmode != B_NK || p.K % 8 || p.lda % 8 || p.ldb % 8))
+    return tatt_set_error("tc2_gemm: operand planes need amode=row, bmode=NK, K/lda/ldb multiples of 8");
   const bool mn = (amode == A_COL || amode == A_IM2COL_T);
   if (mn && bmode != B_KN) return -1;
   Tc2P q = {};
@@ -482,9 +496,9 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
   if (amode == A_ROW) {
     if (p.K % 8) return -1;
     kind = K2_DENSE_K;
-    q.lda = p.K;
-    q.sA = (long long)p.M * p.K;
-    nA = q.sA * p.batch;
+    q.lda = a_pl ? p.lda : p.K;
+    q.sA = a_pl ? p.sA : (long long)p.M * p.K;
+    nA = a_pl ? 0 : q.sA * p.batch;
   } else if (amode == A_IM2COL) {
     if (p.cC % 8 || p.batch != 1) return -1;
     kind = K2_IM2COL_K;
@@ -499,33 +513,49 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
     kind = K2_IM2COL_MN;
     nA = (long long)p.K * p.cC;            // K = pixels
   }
-  if (!mn) {
+  if (b_pl) {
+    q.ldb = p.ldb;
+    q.sB = p.sB;
+  } else if (!mn) {
     q.ldb = rup8(p.K);
     q.sB = (long long)p.N * q.ldb;
   } else {
     q.ldb = rup8(p.N);
     q.sB = (long long)p.K * q.ldb;
   }
-  nB = q.sB * p.batch;
+  nB = b_pl ? 0 : q.sB * p.batch;
   const long long nA8 = rup8(nA), nB8 = rup8(nB);
-  if ((long long)sizeof(__nv_bfloat16) * 2 * (nA8 + nB8) > ws_bytes) return -1;
+  if (nA8 + nB8 > 0 && (ws == nullptr || (long long)sizeof(__nv_bfloat16) * 2 * (nA8 + nB8) > ws_bytes)) {
+    if (a_pl || b_pl) return tatt_set_error("tc2_gemm: workspace too small");
+    return -1;
+  }
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ws);
-  if (!aligned16(base)) return -1;
+  if (nA8 + nB8 > 0 && !aligned16(base)) return -1;
   __nv_bfloat16 *Ahi = base, *Alo = base + nA8, *Bhi = base + 2 * nA8, *Blo = base + 2 * nA8 + nB8;
+  if (a_pl) {
+    Ahi = reinterpret_cast<__nv_bfloat16*>(const_cast<float*>(p.A));
+    Alo = Ahi + p.loA;
+  }
+  if (b_pl) {
+    Bhi = reinterpret_cast<__nv_bfloat16*>(const_cast<float*>(p.B));
+    Blo = Bhi + p.loB;
+  }
 
   // ---- split passes
   for (int b = 0; b < p.batch; ++b) {
     const float* Ab = p.A + (long long)b * p.sA;
     const float* Bb = p.B + (long long)b * p.sB;
     int rc = 0;
-    if (kind == K2_DENSE_K)
+    if (a_pl) {
+    } else if (kind == K2_DENSE_K)
       rc = split_dense(Ab, p.lda, p.M, p.K, p.K, Ahi + b * q.sA, Alo + b * q.sA, st);
     else if (kind == K2_DENSE_MN)
       rc = split_dense(Ab, p.lda, p.K, p.M, (int)q.lda, Ahi + b * q.sA, Alo + b * q.sA, st);
     else if (b == 0)
       rc = split_dense(Ab, p.cC, nA / p.cC, p.cC, p.cC, Ahi, Alo, st);
     if (rc) return rc;
-    if (!mn) {
+    if (b_pl) {
+    } else if (!mn) {
       if (bmode == B_NK)
         rc = split_dense(Bb, p.ldb, p.N, p.K, (int)q.ldb, Bhi + b * q.sB, Blo + b * q.sB, st);
       else

@@ -11,7 +11,7 @@ from . import _cabi
 
 Tensor = torch.Tensor
 ACT_NONE, ACT_RELU, ACT_MISH = 0, 1, 2
-F_ACCUM, F_RELU, F_SPLITK, F_ZEROC, F_FP32 = 1, 2, 4, 64, 128
+F_ACCUM, F_RELU, F_SPLITK, F_ZEROC, F_FP32, F_APLANES, F_BPLANES = 1, 2, 4, 64, 128, 256, 512
 _precision_flag = 0      # OR-ed into every GEMM / conv call; F_FP32 inside `full_fp32()`
 
 
@@ -71,12 +71,31 @@ def empty(*shape, like: Tensor) -> Tensor:
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm(amode: int, bmode: int, A: Tensor, lda: int, B: Tensor, ldb: int, C: Tensor, ldc: int,
          bias: Optional[Tensor], M: int, N: int, K: int, flags: int = 0, batch: int = 1, sA: int = 0, sB: int = 0,
-         sC: int = 0, sBias: int = 0) -> None:
+         sC: int = 0, sBias: int = 0, loA: int = 0, loB: int = 0) -> None:
+    """flags & F_APLANES / F_BPLANES: A / B are bf16 hi planes (see Planes), lo plane at +loA / +loB elements."""
     ws, wsb = (None, 0)
-    if M >= 32 and K >= 32 and N > 4:
+    if M >= 32 and K >= 32 and N > 4 and not (flags & F_APLANES and flags & F_BPLANES):
         ws, wsb = _ws(C, batch * (_r8(M) * _r8(K) + _r8(N) * _r8(K)))
     _cabi.call("tatt_gemm", amode, bmode, _p(A), lda, _p(B), ldb, _p(C), ldc, _p(bias), M, N, K, batch, sA, sB,
-               sC, sBias, flags | _precision_flag, _p(ws), wsb, _stream())
+               sC, sBias, flags | _precision_flag, loA, loB, _p(ws), wsb, _stream())
+
+
+class Planes:
+    """bf16 hi/lo planes of an fp32 operand reused by many GEMMs: one bf16 tensor [2, *shape] (hi, lo)."""
+
+    def __init__(self, shape, like: Tensor, zero: bool = False):
+        self.t = torch.empty((2,) + tuple(shape), dtype=torch.bfloat16, device=like.device)
+        self.lo_off = self.t[0].numel()
+        if zero:
+            _cabi.call("tatt_memset0", _p(self.t), self.t.numel() * 2, _stream())
+
+    def split_from(self, src2d: Tensor, dst_index=None, transpose: bool = False) -> None:
+        """src2d [rows, cols] fp32 -> planes[dst_index] ([rows, cols] or, transposed, [cols, rows]); cols % 8 == 0"""
+        rows, cols, ld = _rows(src2d)
+        hi = self.t[0] if dst_index is None else self.t[0][dst_index]
+        lo = self.t[1] if dst_index is None else self.t[1][dst_index]
+        assert (rows if transpose else cols) % 8 == 0
+        _cabi.call("tatt_split_bf16", _p(src2d), ld, rows, cols, 1 if transpose else 0, _p(hi), _p(lo), _stream())
 
 
 def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], out: Optional[Tensor] = None, accumulate: bool = False,

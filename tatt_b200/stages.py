@@ -191,11 +191,27 @@ def rpe_stage(init_factor: torch.nn.Embedding, gru: torch.nn.GRU, N: int, H: int
         GH = ops.empty(2, Wd, 3 * Hd, like=emb)
         QPOS = ops.empty(N, H * W, C, like=emb)
         sH = (N + 1) * Wd * Hd
+        # operands of the N sequential recurrent GEMMs as pre-split bf16 hi/lo planes: W_hh is split once, the
+        # hidden state is written in plane form by the gate kernel itself
+        fast = Hd % 8 == 0 and Wd >= 32 and not (ops._precision_flag & ops.F_FP32)
+        if fast:
+            WP = ops.Planes((2, 3 * Hd, Hd), emb)
+            for d in range(2):
+                WP.split_from(w_hh[d], d)
+            HP = ops.Planes((2, N + 1, Wd, Hd), emb, zero=True)
         for s in range(N):
-            ops.gemm(0, 1, HALL[0, s], Hd, WHH, Hd, GH, 3 * Hd, BHH, Wd, 3 * Hd, Hd, 0, batch=2, sA=sH,
-                     sB=3 * Hd * Hd, sC=Wd * 3 * Hd, sBias=3 * Hd)
+            if fast:
+                ops.gemm(0, 1, HP.t[0, 0, s], Hd, WP.t, Hd, GH, 3 * Hd, BHH, Wd, 3 * Hd, Hd,
+                         ops.F_APLANES | ops.F_BPLANES, batch=2, sA=sH, sB=3 * Hd * Hd, sC=Wd * 3 * Hd, sBias=3 * Hd,
+                         loA=HP.lo_off, loB=WP.lo_off)
+            else:
+                ops.gemm(0, 1, HALL[0, s], Hd, WHH, Hd, GH, 3 * Hd, BHH, Wd, 3 * Hd, Hd, 0, batch=2, sA=sH,
+                         sB=3 * Hd * Hd, sC=Wd * 3 * Hd, sBias=3 * Hd)
             _cabi.call("tatt_rpe_gate_fwd", GI.data_ptr(), GH.data_ptr(), HALL.data_ptr(),
-                       None if GATES is None else GATES.data_ptr(), QPOS.data_ptr(), s, N, Wd, Hd, C, H, st())
+                       None if GATES is None else GATES.data_ptr(), QPOS.data_ptr(),
+                       HP.t.data_ptr() if fast else None, HP.lo_off if fast else 0, s, N, Wd, Hd, C, H, st())
+        if fast:
+            del HP, WP
 
         def bwd():
             dQ = tape.grad(QPOS)
@@ -204,10 +220,20 @@ def rpe_stage(init_factor: torch.nn.Embedding, gru: torch.nn.GRU, N: int, H: int
             DH = ops.zeros(2, Wd, Hd, like=emb)
             DGI = ops.zeros(2, Wd, 3 * Hd, like=emb)
             DGH = ops.empty(2, N, Wd, 3 * Hd, like=emb)
+            if fast:
+                WTP = ops.Planes((2, Hd, 3 * Hd), emb)              # W_hh^T: B operand [N=Hd][K=3Hd] of dh += dgh W_hh
+                for d in range(2):
+                    WTP.split_from(w_hh[d], d, transpose=True)
+                DP = ops.Planes((2, N, Wd, 3 * Hd), emb)
             for s in range(N - 1, -1, -1):
                 _cabi.call("tatt_rpe_gate_bwd", dQ.data_ptr(), HALL.data_ptr(), GATES.data_ptr(), DH.data_ptr(),
-                           DGI.data_ptr(), DGH.data_ptr(), s, N, Wd, Hd, C, H, st())
-                if s > 0:
+                           DGI.data_ptr(), DGH.data_ptr(), DP.t.data_ptr() if fast else None,
+                           DP.lo_off if fast else 0, s, N, Wd, Hd, C, H, st())
+                if s > 0 and fast:
+                    ops.gemm(0, 1, DP.t[0, 0, s], 3 * Hd, WTP.t, 3 * Hd, DH, Hd, None, Wd, Hd, 3 * Hd,
+                             ops.F_ACCUM | ops.F_APLANES | ops.F_BPLANES, batch=2, sA=N * Wd * 3 * Hd, sB=3 * Hd * Hd,
+                             sC=Wd * Hd, loA=DP.lo_off, loB=WTP.lo_off)
+                elif s > 0:
                     ops.gemm(0, 0, DGH[0, s], 3 * Hd, WHH, Hd, DH, Hd, None, Wd, Hd, 3 * Hd, ops.F_ACCUM, batch=2,
                              sA=N * Wd * 3 * Hd, sB=3 * Hd * Hd, sC=Wd * Hd)
             dWHH = ops.empty(2, 3 * Hd, Hd, like=emb)

@@ -272,13 +272,16 @@ class Tape:
         w_hh = (gru.weight_hh_l0, gru.weight_hh_l0_reverse)
         b_ih = (gru.bias_ih_l0, gru.bias_ih_l0_reverse)
         b_hh = (gru.bias_hh_l0, gru.bias_hh_l0_reverse)
-        gi = ops.empty(P, 192, like=c)
+        wih = ops.empty(192, 64, like=c)          # both directions' input projections as ONE N=192 GEMM
+        bih = ops.empty(192, like=c)
         whh = ops.empty(2, 96, 32, like=c)
         bhh = ops.empty(2, 96, like=c)
         for d in range(2):
-            ops.linear_fwd(c, w_ih[d], b_ih[d], out=gi[:, d * 96:(d + 1) * 96])
+            ops.memcpy(wih[d * 96:(d + 1) * 96], w_ih[d])
+            ops.memcpy(bih[d * 96:(d + 1) * 96], b_ih[d])
             ops.memcpy(whh[d], w_hh[d])
             ops.memcpy(bhh[d], b_hh[d])
+        gi = ops.linear_fwd(c, wih, bih)
         out, gates = ops.gru32_scan_fwd(gi, whh, bhh, nseq, T, s_inner, outer, inner, tstride, save=self.record)
         del gi
 
@@ -287,17 +290,17 @@ class Tape:
             if dout is None:
                 return
             dgi, dgh = ops.gru32_scan_bwd(dout, gates, whh, nseq, T, s_inner, outer, inner, tstride)
-            dc = None
+            dwih = ops.linear_bwd_weight(dgi, c)             # [192, 64]
+            dbih = ops.colsum(dgi)
+            dbhh = ops.colsum(dgh)
             for d in range(2):
-                gi_d = dgi[:, d * 96:(d + 1) * 96]
                 gh_d = dgh[:, d * 96:(d + 1) * 96]
                 hprev = gates[:, d * 160 + 128:d * 160 + 160]
                 self.add_grad(w_hh[d], ops.linear_bwd_weight(gh_d, hprev))
-                self.add_grad(b_hh[d], ops.colsum(gh_d))
-                self.add_grad(w_ih[d], ops.linear_bwd_weight(gi_d, c))
-                self.add_grad(b_ih[d], ops.colsum(gi_d))
-                dc = ops.linear_bwd_data(gi_d, w_ih[d], out=dc, accumulate=d > 0)
-            self.add_grad(c, dc)
+                self.add_grad(b_hh[d], dbhh[d * 96:(d + 1) * 96])
+                self.add_grad(w_ih[d], dwih[d * 96:(d + 1) * 96])
+                self.add_grad(b_ih[d], dbih[d * 96:(d + 1) * 96])
+            self.add_grad(c, ops.linear_bwd_data(dgi, wih))
         self._push(bwd)
         return out
 

@@ -31,7 +31,7 @@ def test_version_arch_and_error_channel(libpath):
     L = _cabi.lib()
     assert L.tatt_version() >= 100
     assert L.tatt_arch() == 1                       # compiled with -gencode arch=compute_100a,code=sm_100a
-    rc = L.tatt_gemm(7, 0, None, 1, None, 1, None, 1, None, 4, 4, 4, 1, 0, 0, 0, 0, 0, None, 0, None)
+    rc = L.tatt_gemm(7, 0, None, 1, None, 1, None, 1, None, 4, 4, 4, 1, 0, 0, 0, 0, 0, 0, 0, None, 0, None)
     assert rc != 0 and "amode" in _cabi.last_error()
     with pytest.raises(RuntimeError, match="Lk"):
         _cabi.call("tatt_mha64_fwd", None, None, None, None, None, 1, 8, 40, 0.0, None, 0, None)
