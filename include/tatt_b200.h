@@ -38,9 +38,10 @@ int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* 
 /* Pre-split bf16 hi/lo operand planes (for operands reused by many GEMMs, e.g. W_hh over the RPE recurrence):
  * planes[rows][round8(cols)], or with transpose=1 planes[cols][round8(rows)].  Pass them to tatt_gemm with
  * flags 256 (A is the hi plane, lo plane at A + loA bf16 elements, lda/sA in plane elements) / 512 (same for B);
- * requires amode 0, bmode 1. */
+ * operand pairs (amode 0, bmode 1) or (amode 1, bmode 0).  colsum (optional, non-transposed only): out[c] =
+ * sum_r src[r][c], i.e. the bias gradient for free while the gradient matrix is being split. */
 int tatt_split_bf16(const float* src, long long ld, long long rows, int cols, int transpose, void* hi, void* lo,
-                    void* stream);
+                    float* colsum, void* stream);
 /* out[c] (+)= sum_r X[r*ldx + c] */
 int tatt_colsum(const float* X, long long ldx, float* out, long long P, int C, int zero_first, void* stream);
 

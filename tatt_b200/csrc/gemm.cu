@@ -604,7 +604,13 @@ int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* 
   p.ws = ws;
   p.ws_bytes = ws_bytes;
   if (flags & (F_APLANES | F_BPLANES)) {
-    int rc = tatt_tc2_gemm_launch(p, amode, bmode, false, ws, ws_bytes, (cudaStream_t)stream);
+    const bool want = (flags & F_ATOMIC) != 0;
+    if (want && (flags & F_ZEROC)) {
+      TATT_REQUIRE(ldc == N && (batch == 1 || sC == (long long)M * N), "tatt_gemm: F_ZEROC needs a dense C");
+      TATT_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)batch * M * N, (cudaStream_t)stream));
+    }
+    if ((p.ldc % 4 == 0) && ((((uintptr_t)C) & 15) == 0) && (p.sC % 4 == 0)) p.flags |= F_VECC;
+    int rc = tatt_tc2_gemm_launch(p, amode, bmode, want, ws, ws_bytes, (cudaStream_t)stream);
     if (rc < 0) return tatt_set_error("tatt_gemm: operand planes need the tcgen05 path");
     return rc;
   }
@@ -619,8 +625,8 @@ int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* 
 // bf16 hi/lo operand planes for tatt_gemm flags 256 (A) / 512 (B): planes[rows][round8(cols)] or, transposed,
 // planes[cols][round8(rows)]
 int tatt_split_bf16(const float* src, long long ld, long long rows, int cols, int transpose, void* hi, void* lo,
-                    void* stream) {
-  return tatt_tc2_split(src, ld, rows, cols, transpose, hi, lo, (cudaStream_t)stream);
+                    float* colsum, void* stream) {
+  return tatt_tc2_split(src, ld, rows, cols, transpose, hi, lo, colsum, (cudaStream_t)stream);
 }
 
 int tatt_colsum(const float* X, long long ldx, float* out, long long P, int C, int zero_first, void* stream) {

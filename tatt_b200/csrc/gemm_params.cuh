@@ -54,7 +54,7 @@ struct GemmP {
 // tcgen05 path (tc_gemm.cu); returns 0 on success, -1 if the shape is not eligible (caller falls through to FFMA)
 int tatt_tc_gemm_launch(GemmP p, int amode, int bmode, bool want_split, cudaStream_t st);
 int tatt_tc2_split(const float* src, long long ld, long long rows, int cols, int transpose, void* hi, void* lo,
-                   cudaStream_t st);
+                   float* colsum, cudaStream_t st);
 // v2 (tc2_gemm.cu): operands pre-split into bf16 planes in `ws`; same return convention
 int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* ws, long long ws_bytes,
                          cudaStream_t st);

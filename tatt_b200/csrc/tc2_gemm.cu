@@ -408,6 +408,52 @@ __global__ void split_dense_kernel(const float* __restrict__ src, long long ld, 
     *reinterpret_cast<uint2*>(lo + r * colsP + c) = lv;
   }
 }
+// same split, plus out[c] += sum_r src[r][c] (the bias gradient) -- block = (colsP/4) x R threads
+__global__ void split_colsum_kernel(const float* __restrict__ src, long long ld, long long rows, int cols, int colsP,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                    float* __restrict__ colsum, int rows_per_block, int vec) {
+  extern __shared__ float red[];          // [blockDim.y][colsP]
+  const int c = threadIdx.x * 4;
+  long long r0 = (long long)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* s = src + r * ld + c;
+    if (vec && c + 3 < cols) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(s));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < cols) v[j] = __ldg(s + j);
+    }
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      split1(v[j], h[j], l[j]);
+      a[j] += v[j];
+    }
+    uint2 hv, lv;
+    hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+    lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(hi + r * colsP + c) = hv;
+    *reinterpret_cast<uint2*>(lo + r * colsP + c) = lv;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[threadIdx.y * colsP + c + j] = a[j];
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = 0.f;
+      for (int y = 0; y < (int)blockDim.y; ++y) t += red[y * colsP + c + j];
+      if (c + j < cols) atomicAdd(colsum + c + j, t);
+    }
+  }
+}
 // src [K][N] (row stride ld) -> planes [N][Kp]   (small weight matrices)
 __global__ void split_transpose_kernel(const float* __restrict__ src, long long ld, int K, int N, int Kp,
                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
@@ -472,7 +518,25 @@ static int launch_kind(const Tc2P& q, cudaStream_t st) {
 
 // planes [rows][rup8(cols)] (transpose == 0) or [cols][rup8(rows)] (transpose == 1), zero padded
 int tatt_tc2_split(const float* src, long long ld, long long rows, int cols, int transpose, void* hi, void* lo,
-                   cudaStream_t st) {
+                   float* colsum, cudaStream_t st) {
+  if (!transpose && colsum) {
+    const int colsP = (int)rup8(cols);
+    TATT_REQUIRE(colsP <= 1024, "split_bf16: fused column sums need cols <= 1024");
+    TATT_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * cols, st));
+    if (rows <= 0) return 0;
+    const int tx = colsP / 4;
+    int ty = 256 / tx;
+    if (ty < 1) ty = 1;
+    int rpb = 256;
+    if (rows > 256LL * 148 * 8) rpb = (int)((rows + 148 * 8 - 1) / (148 * 8));
+    int blocks = (int)((rows + rpb - 1) / rpb);
+    int vec = (ld % 4 == 0 && aligned16(src)) ? 1 : 0;
+    split_colsum_kernel<<<blocks, dim3(tx, ty), sizeof(float) * ty * colsP, st>>>(
+        src, ld, rows, cols, colsP, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rpb, vec);
+    TATT_LAUNCH_CHECK("split_colsum_kernel");
+    return 0;
+  }
+  TATT_REQUIRE(!colsum, "split_bf16: column sums are not available for the transposed split");
   if (!transpose)
     return split_dense(src, ld, rows, cols, (int)rup8(cols), (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, st);
   return split_transpose(src, ld, (int)rows, cols, (int)rup8(rows), (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, st);
@@ -486,8 +550,13 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
     if (a_pl || b_pl) return tatt_set_error("tc2_gemm: pre-split operand planes given for an ineligible shape");
     return -1;
   }
-  if ((a_pl || b_pl) && (amode != A_ROW || bmode != B_NK || p.K % 8 || p.lda % 8 || p.ldb % 8))
-    return tatt_set_error("tc2_gemm: operand planes need amode=row, bmode=NK, K/lda/ldb multiples of 8");
+  if (a_pl && ((amode != A_ROW && amode != A_COL) || p.lda % 8))
+    return tatt_set_error("tc2_gemm: A planes need amode row/col and lda %% 8 == 0");
+  if (b_pl && (!((amode == A_ROW && bmode == B_NK) || (amode == A_COL && bmode == B_KN)) || p.ldb % 8))
+    return tatt_set_error("tc2_gemm: B planes need (row,NK) or (col,KN) operands and ldb %% 8 == 0");
+  // single-pass small GEMMs (one N tile, one or two k-tiles): the in-loop split of v1 moves fewer bytes than a
+  // separate split pass
+  if (!a_pl && !b_pl && amode == A_ROW && p.N <= 64 && p.K <= 128 && p.batch == 1) return -1;
   const bool mn = (amode == A_COL || amode == A_IM2COL_T);
   if (mn && bmode != B_KN) return -1;
   Tc2P q = {};
@@ -505,9 +574,9 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
     nA = (long long)(p.M) * p.cC;          // M = nimg*H*W pixels
   } else if (amode == A_COL) {
     kind = K2_DENSE_MN;
-    q.lda = rup8(p.M);
-    q.sA = (long long)p.K * q.lda;
-    nA = q.sA * p.batch;
+    q.lda = a_pl ? p.lda : rup8(p.M);
+    q.sA = a_pl ? p.sA : (long long)p.K * q.lda;
+    nA = a_pl ? 0 : q.sA * p.batch;
   } else {
     if (p.cC % 64 || p.batch != 1) return -1;
     kind = K2_IM2COL_MN;

@@ -95,11 +95,36 @@ class Planes:
         hi = self.t[0] if dst_index is None else self.t[0][dst_index]
         lo = self.t[1] if dst_index is None else self.t[1][dst_index]
         assert (rows if transpose else cols) % 8 == 0
-        _cabi.call("tatt_split_bf16", _p(src2d), ld, rows, cols, 1 if transpose else 0, _p(hi), _p(lo), _stream())
+        _cabi.call("tatt_split_bf16", _p(src2d), ld, rows, cols, 1 if transpose else 0, _p(hi), _p(lo), None,
+                   _stream())
+
+
+class MatPlanes:
+    """bf16 hi/lo planes of a [rows, cols] fp32 matrix (row stride `ld`, lo plane `lo_off` elements after hi).
+    One split pass serves every GEMM that consumes the matrix (forward, data-gradient and weight-gradient)."""
+
+    def __init__(self, hi: Tensor, lo_off: int, ld: int):
+        self.hi, self.lo_off, self.ld = hi, lo_off, ld
+        self.rows, self.cols = hi.shape
+
+    def slice_cols(self, a: int, b: int) -> "MatPlanes":
+        assert a % 8 == 0
+        return MatPlanes(self.hi[:, a:b], self.lo_off, self.ld)
+
+
+def split_matrix(x2: Tensor, colsum_out: Optional[Tensor] = None) -> Optional[MatPlanes]:
+    """Split once for the tcgen05 engine; None when the matrix is not eligible (fp32 mode, odd shapes) -- callers
+    then use the plain fp32 entry points (and compute the column sum separately)."""
+    rows, cols, ld = _rows(x2)
+    if (_precision_flag & F_FP32) or cols % 8 or cols < 32 or rows < 32:
+        return None
+    t = torch.empty(2, rows, cols, dtype=torch.bfloat16, device=x2.device)
+    _cabi.call("tatt_split_bf16", _p(x2), ld, rows, cols, 0, _p(t[0]), _p(t[1]), _p(colsum_out), _stream())
+    return MatPlanes(t[0], rows * cols, cols)
 
 
 def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], out: Optional[Tensor] = None, accumulate: bool = False,
-               relu: bool = False) -> Tensor:
+               relu: bool = False, xP: Optional[MatPlanes] = None) -> Tensor:
     """out[M,N] (=|+=) x[M,K] @ w[N,K]^T + b"""
     M, K, ldx = _rows(x)
     N, K2, ldw = _rows(w)
@@ -107,11 +132,16 @@ def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], out: Optional[Tensor] 
     if out is None:
         out = empty(M, N, like=x)
     _, _, ldo = _rows(out)
-    gemm(0, 1, x, ldx, w, ldw, out, ldo, b, M, N, K, (F_ACCUM if accumulate else 0) | (F_RELU if relu else 0))
+    fl = (F_ACCUM if accumulate else 0) | (F_RELU if relu else 0)
+    if xP is not None and N > 4:
+        gemm(0, 1, xP.hi, xP.ld, w, ldw, out, ldo, b, M, N, K, fl | F_APLANES, loA=xP.lo_off)
+    else:
+        gemm(0, 1, x, ldx, w, ldw, out, ldo, b, M, N, K, fl)
     return out
 
 
-def linear_bwd_data(dy: Tensor, w: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+def linear_bwd_data(dy: Tensor, w: Tensor, out: Optional[Tensor] = None, accumulate: bool = False,
+                    dyP: Optional[MatPlanes] = None) -> Tensor:
     """out[M,K] (=|+=) dy[M,N] @ w[N,K]"""
     M, N, lddy = _rows(dy)
     N2, K, ldw = _rows(w)
@@ -119,11 +149,16 @@ def linear_bwd_data(dy: Tensor, w: Tensor, out: Optional[Tensor] = None, accumul
     if out is None:
         out = empty(M, K, like=dy)
     _, _, ldo = _rows(out)
-    gemm(0, 0, dy, lddy, w, ldw, out, ldo, None, M, K, N, F_ACCUM if accumulate else 0)
+    fl = F_ACCUM if accumulate else 0
+    if dyP is not None and K > 4:
+        gemm(0, 0, dyP.hi, dyP.ld, w, ldw, out, ldo, None, M, K, N, fl | F_APLANES, loA=dyP.lo_off)
+    else:
+        gemm(0, 0, dy, lddy, w, ldw, out, ldo, None, M, K, N, fl)
     return out
 
 
-def linear_bwd_weight(dy: Tensor, x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+def linear_bwd_weight(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, dyP: Optional[MatPlanes] = None,
+                      xP: Optional[MatPlanes] = None) -> Tensor:
     """out[N,K] += dy[M,N]^T @ x[M,K]  (split-K atomics; `out` must be zero-filled if given)"""
     M, N, lddy = _rows(dy)
     M2, K, ldx = _rows(x)
@@ -133,7 +168,14 @@ def linear_bwd_weight(dy: Tensor, x: Tensor, out: Optional[Tensor] = None) -> Te
         out = empty(N, K, like=dy)
         flags |= F_ZEROC
     _, _, ldo = _rows(out)
-    gemm(1, 0, dy, lddy, x, ldx, out, ldo, None, N, K, M, flags)
+    ok = N >= 32 and K > 4 and M >= 32
+    A, lda, loA = (dyP.hi, dyP.ld, dyP.lo_off) if (dyP is not None and ok) else (dy, lddy, 0)
+    B, ldb, loB = (xP.hi, xP.ld, xP.lo_off) if (xP is not None and ok) else (x, ldx, 0)
+    if dyP is not None and ok:
+        flags |= F_APLANES
+    if xP is not None and ok:
+        flags |= F_BPLANES
+    gemm(1, 0, A, lda, B, ldb, out, ldo, None, N, K, M, flags, loA=loA, loB=loB)
     return out
 
 

@@ -49,9 +49,21 @@ class Tape:
             self._ops.append(fn)
 
     # ------------------------------------------------------------------ dense layers
+    def _split_grad(self, dy: Tensor, bias: Optional[Tensor]):
+        """bf16 planes of a gradient matrix (shared by its data- and weight-gradient GEMMs); the bias gradient
+        (column sums) is produced by the same pass."""
+        db = ops.empty(dy.shape[1], like=dy) if bias is not None else None
+        dyP = ops.split_matrix(dy, db)
+        if dyP is None and bias is not None:
+            ops.colsum(dy, out=db)
+        if bias is not None:
+            self.add_grad(bias, db)
+        return dyP
+
     def linear(self, x: Tensor, W: Tensor, b: Optional[Tensor], relu: bool = False) -> Tensor:
         """x [M,K] @ W[N,K]^T + b (optionally ReLU)"""
-        y = ops.linear_fwd(x, W, b, relu=relu)
+        xP = ops.split_matrix(x) if self.record else None
+        y = ops.linear_fwd(x, W, b, relu=relu, xP=xP)
 
         def bwd():
             dy = self.grad(y)
@@ -59,10 +71,9 @@ class Tape:
                 return
             if relu:
                 dy = ops.relu_bwd(y, dy)
-            self.add_grad(W, ops.linear_bwd_weight(dy, x))
-            if b is not None:
-                self.add_grad(b, ops.colsum(dy))
-            self.add_grad(x, ops.linear_bwd_data(dy, W))
+            dyP = self._split_grad(dy, b)
+            self.add_grad(W, ops.linear_bwd_weight(dy, x, dyP=dyP, xP=xP))
+            self.add_grad(x, ops.linear_bwd_data(dy, W, dyP=dyP))
         self._push(bwd)
         return y
 
@@ -72,24 +83,27 @@ class Tape:
         W = W4.view(W4.shape[0], -1)
         y = None
         off = 0
+        pls = []
         for t in parts:
             ci = t.shape[1]
-            y = ops.linear_fwd(t, W[:, off:off + ci], b if off == 0 else None, out=y, accumulate=off > 0)
+            tP = ops.split_matrix(t) if self.record else None
+            pls.append(tP)
+            y = ops.linear_fwd(t, W[:, off:off + ci], b if off == 0 else None, out=y, accumulate=off > 0, xP=tP)
             off += ci
 
         def bwd():
             dy = self.grad(y)
             if dy is None:
                 return
+            dyP = self._split_grad(dy, b)
             dW = ops.zeros(W.shape[0], W.shape[1], like=dy)
             o = 0
-            for t in parts:
+            for t, tP in zip(parts, pls):
                 ci = t.shape[1]
-                ops.linear_bwd_weight(dy, t, out=dW[:, o:o + ci])
-                self.add_grad(t, ops.linear_bwd_data(dy, W[:, o:o + ci]))
+                ops.linear_bwd_weight(dy, t, out=dW[:, o:o + ci], dyP=dyP, xP=tP)
+                self.add_grad(t, ops.linear_bwd_data(dy, W[:, o:o + ci], dyP=dyP))
                 o += ci
             self.add_grad(W4, dW.view_as(W4))
-            self.add_grad(b, ops.colsum(dy))
         self._push(bwd)
         return y
 
@@ -281,7 +295,8 @@ class Tape:
             ops.memcpy(bih[d * 96:(d + 1) * 96], b_ih[d])
             ops.memcpy(whh[d], w_hh[d])
             ops.memcpy(bhh[d], b_hh[d])
-        gi = ops.linear_fwd(c, wih, bih)
+        cP = ops.split_matrix(c) if self.record else None
+        gi = ops.linear_fwd(c, wih, bih, xP=cP)
         out, gates = ops.gru32_scan_fwd(gi, whh, bhh, nseq, T, s_inner, outer, inner, tstride, save=self.record)
         del gi
 
@@ -290,17 +305,22 @@ class Tape:
             if dout is None:
                 return
             dgi, dgh = ops.gru32_scan_bwd(dout, gates, whh, nseq, T, s_inner, outer, inner, tstride)
-            dwih = ops.linear_bwd_weight(dgi, c)             # [192, 64]
-            dbih = ops.colsum(dgi)
-            dbhh = ops.colsum(dgh)
+            dbih, dbhh = ops.empty(192, like=c), ops.empty(192, like=c)
+            dgiP, dghP = ops.split_matrix(dgi, dbih), ops.split_matrix(dgh, dbhh)
+            if dgiP is None:
+                ops.colsum(dgi, out=dbih)
+            if dghP is None:
+                ops.colsum(dgh, out=dbhh)
+            dwih = ops.linear_bwd_weight(dgi, c, dyP=dgiP, xP=cP)             # [192, 64]
             for d in range(2):
                 gh_d = dgh[:, d * 96:(d + 1) * 96]
                 hprev = gates[:, d * 160 + 128:d * 160 + 160]
-                self.add_grad(w_hh[d], ops.linear_bwd_weight(gh_d, hprev))
+                ghP = dghP.slice_cols(d * 96, (d + 1) * 96) if dghP is not None else None
+                self.add_grad(w_hh[d], ops.linear_bwd_weight(gh_d, hprev, dyP=ghP))
                 self.add_grad(b_hh[d], dbhh[d * 96:(d + 1) * 96])
                 self.add_grad(w_ih[d], dwih[d * 96:(d + 1) * 96])
                 self.add_grad(b_ih[d], dbih[d * 96:(d + 1) * 96])
-            self.add_grad(c, ops.linear_bwd_data(dgi, wih))
+            self.add_grad(c, ops.linear_bwd_data(dgi, wih, dyP=dgiP))
         self._push(bwd)
         return out
 
@@ -309,9 +329,19 @@ class Tape:
         """nn.MultiheadAttention(64, 4) on token-major [N*L, 64] inputs -> (out [N*Lq,64], weights)."""
         Win, bin_ = attn.in_proj_weight, attn.in_proj_bias
         Wo, bo = attn.out_proj.weight, attn.out_proj.bias
-        q = ops.linear_fwd(q_in, Win[0:64], bin_[0:64])
-        k = ops.linear_fwd(k_in, Win[64:128], bin_[64:128])
-        v = ops.linear_fwd(v_in, Win[128:192], bin_[128:192])
+        srcs = (q_in, k_in, v_in)
+        sP = [None, None, None]
+        if self.record:
+            for i in range(3):
+                for j in range(i):
+                    if srcs[i] is srcs[j]:
+                        sP[i] = sP[j]
+                        break
+                else:
+                    sP[i] = ops.split_matrix(srcs[i])
+        q = ops.linear_fwd(q_in, Win[0:64], bin_[0:64], xP=sP[0])
+        k = ops.linear_fwd(k_in, Win[64:128], bin_[64:128], xP=sP[1])
+        v = ops.linear_fwd(v_in, Win[128:192], bin_[128:192], xP=sP[2])
         if pdrop <= 0.0 or rng is None:
             pdrop, rng_ = 0.0, None
         else:
@@ -323,16 +353,18 @@ class Tape:
             dy = self.grad(y)
             if dy is None:
                 return
-            self.add_grad(Wo, ops.linear_bwd_weight(dy, a))
-            self.add_grad(bo, ops.colsum(dy))
-            da = ops.linear_bwd_data(dy, Wo)
+            dyP = self._split_grad(dy, bo)
+            self.add_grad(Wo, ops.linear_bwd_weight(dy, a, dyP=dyP))
+            da = ops.linear_bwd_data(dy, Wo, dyP=dyP)
             dq, dk, dv = ops.mha_bwd(q, k, v, da, N, Lq, Lk, pdrop, rng_, site)
             dWin = ops.zeros(192, 64, like=dy)
             dbin = ops.empty(192, like=dy)
             for i, (g, src) in enumerate(((dq, q_in), (dk, k_in), (dv, v_in))):
-                ops.linear_bwd_weight(g, src, out=dWin[i * 64:(i + 1) * 64])
-                ops.colsum(g, out=dbin[i * 64:(i + 1) * 64])
-                self.add_grad(src, ops.linear_bwd_data(g, Win[i * 64:(i + 1) * 64]))
+                gP = ops.split_matrix(g, dbin[i * 64:(i + 1) * 64])
+                if gP is None:
+                    ops.colsum(g, out=dbin[i * 64:(i + 1) * 64])
+                ops.linear_bwd_weight(g, src, out=dWin[i * 64:(i + 1) * 64], dyP=gP, xP=sP[i])
+                self.add_grad(src, ops.linear_bwd_data(g, Win[i * 64:(i + 1) * 64], dyP=gP))
             self.add_grad(Win, dWin)
             self.add_grad(bin_, dbin)
         self._push(bwd)
