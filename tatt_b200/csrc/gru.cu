@@ -17,6 +17,10 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16* hi, __nv_bflo
   lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
+// fast activations for the recurrences: MUFU ex2/rcp based, abs error ~1e-6 (tolerance of the path: 1e-3)
+__device__ __forceinline__ float fsigmoid(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * x)); }
+
 // GI    [rows][192]  = [dir][gate][32]   (x W_ih^T + b_ih, both directions)
 // OUT   [rows][64]   = [dir][32]
 // GATES [rows][320]  = [dir][r,z,n,ghn,hprev][32]   (saved for the backward; may be NULL)
@@ -25,7 +29,9 @@ gru32_scan_fwd_kernel(const float* __restrict__ GI, const float* __restrict__ Wh
                       const float* __restrict__ bhh, float* __restrict__ OUT, float* __restrict__ GATES,
                       int nseq, int T, int s_inner, long long outer_stride, long long inner_stride,
                       long long t_stride) {
+  __shared__ __align__(16) float hs[4][32];     // per-warp broadcast buffer for the hidden state
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int dir = (int)(gw & 1);
   const long long seq = gw >> 1;
@@ -73,22 +79,32 @@ gru32_scan_fwd_kernel(const float* __restrict__ GI, const float* __restrict__ Wh
         }
         float ar = br, az = bz, an = bn;
         float ar2 = 0.f, az2 = 0.f, an2 = 0.f;          // two partial chains halve the FMA dependency depth
+        // broadcast h through shared memory: 1 STS + 8 LDS.128 instead of 32 shuffles
+        __syncwarp();
+        hs[wib][lane] = h;
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          float h0 = __shfl_sync(0xffffffffu, h, k), h1 = __shfl_sync(0xffffffffu, h, k + 1);
-          ar = fmaf(wr[k], h0, ar);
-          az = fmaf(wz[k], h0, az);
-          an = fmaf(wn[k], h0, an);
-          ar2 = fmaf(wr[k + 1], h1, ar2);
-          az2 = fmaf(wz[k + 1], h1, az2);
-          an2 = fmaf(wn[k + 1], h1, an2);
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 hv = *reinterpret_cast<const float4*>(&hs[wib][k4 * 4]);
+          ar = fmaf(wr[k4 * 4 + 0], hv.x, ar);
+          az = fmaf(wz[k4 * 4 + 0], hv.x, az);
+          an = fmaf(wn[k4 * 4 + 0], hv.x, an);
+          ar2 = fmaf(wr[k4 * 4 + 1], hv.y, ar2);
+          az2 = fmaf(wz[k4 * 4 + 1], hv.y, az2);
+          an2 = fmaf(wn[k4 * 4 + 1], hv.y, an2);
+          ar = fmaf(wr[k4 * 4 + 2], hv.z, ar);
+          az = fmaf(wz[k4 * 4 + 2], hv.z, az);
+          an = fmaf(wn[k4 * 4 + 2], hv.z, an);
+          ar2 = fmaf(wr[k4 * 4 + 3], hv.w, ar2);
+          az2 = fmaf(wz[k4 * 4 + 3], hv.w, az2);
+          an2 = fmaf(wn[k4 * 4 + 3], hv.w, an2);
         }
         ar += ar2;
         az += az2;
         an += an2;
-        float r = sigmoid_f(gr + ar);
-        float z = sigmoid_f(gz + az);
-        float n = tanhf(gn + r * an);
+        float r = fsigmoid(gr + ar);
+        float z = fsigmoid(gz + az);
+        float n = ftanh(gn + r * an);
         float hn = n + z * (h - n);
         OUT[row * 64 + dir * 32 + lane] = hn;
         if (GATES) {
@@ -111,7 +127,9 @@ __global__ void __launch_bounds__(128)
 gru32_scan_bwd_kernel(const float* __restrict__ dOUT, const float* __restrict__ GATES,
                       const float* __restrict__ Whh, float* __restrict__ dGI, float* __restrict__ dGH, int nseq,
                       int T, int s_inner, long long outer_stride, long long inner_stride, long long t_stride) {
+  __shared__ __align__(16) float gs[4][96];     // per-warp broadcast buffer: dpr | dpz | dhn
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int dir = (int)(gw & 1);
   const long long seq = gw >> 1;
@@ -167,11 +185,28 @@ gru32_scan_bwd_kernel(const float* __restrict__ dOUT, const float* __restrict__ 
         o2[32] = dpz;
         o2[64] = dhn;
         float acc = go * z, acc2 = 0.f, acc3 = 0.f;
+        __syncwarp();
+        gs[wib][lane] = dpr;
+        gs[wib][32 + lane] = dpz;
+        gs[wib][64 + lane] = dhn;
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          acc = fmaf(wc[k], __shfl_sync(0xffffffffu, dpr, k), acc);
-          acc2 = fmaf(wc[32 + k], __shfl_sync(0xffffffffu, dpz, k), acc2);
-          acc3 = fmaf(wc[64 + k], __shfl_sync(0xffffffffu, dhn, k), acc3);
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 a = *reinterpret_cast<const float4*>(&gs[wib][k4 * 4]);
+          const float4 b = *reinterpret_cast<const float4*>(&gs[wib][32 + k4 * 4]);
+          const float4 c = *reinterpret_cast<const float4*>(&gs[wib][64 + k4 * 4]);
+          acc = fmaf(wc[k4 * 4 + 0], a.x, acc);
+          acc2 = fmaf(wc[32 + k4 * 4 + 0], b.x, acc2);
+          acc3 = fmaf(wc[64 + k4 * 4 + 0], c.x, acc3);
+          acc = fmaf(wc[k4 * 4 + 1], a.y, acc);
+          acc2 = fmaf(wc[32 + k4 * 4 + 1], b.y, acc2);
+          acc3 = fmaf(wc[64 + k4 * 4 + 1], c.y, acc3);
+          acc = fmaf(wc[k4 * 4 + 2], a.z, acc);
+          acc2 = fmaf(wc[32 + k4 * 4 + 2], b.z, acc2);
+          acc3 = fmaf(wc[64 + k4 * 4 + 2], c.z, acc3);
+          acc = fmaf(wc[k4 * 4 + 3], a.w, acc);
+          acc2 = fmaf(wc[32 + k4 * 4 + 3], b.w, acc2);
+          acc3 = fmaf(wc[64 + k4 * 4 + 3], c.w, acc3);
         }
         dh = acc + acc2 + acc3;
         row += step_stride;
