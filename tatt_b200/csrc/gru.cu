@@ -18,25 +18,30 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16* hi, __nv_bflo
 }
 
 // fast activations for the recurrences: MUFU ex2/rcp based, abs error ~1e-6 (tolerance of the path: 1e-3)
-__device__ __forceinline__ float fsigmoid(float x) { return __frcp_rn(1.f + __expf(-x)); }
-__device__ __forceinline__ float ftanh(float x) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * x)); }
+__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // GI    [rows][192]  = [dir][gate][32]   (x W_ih^T + b_ih, both directions)
 // OUT   [rows][64]   = [dir][32]
 // GATES [rows][320]  = [dir][r,z,n,ghn,hprev][32]   (saved for the backward; may be NULL)
+// Each warp advances TWO sequences of the same direction in lock-step: the W_hh rows in registers are shared and
+// the two independent dependency chains double the ILP of this latency-bound recurrence.
 __global__ void __launch_bounds__(128)
 gru32_scan_fwd_kernel(const float* __restrict__ GI, const float* __restrict__ Whh,
                       const float* __restrict__ bhh, float* __restrict__ OUT, float* __restrict__ GATES,
                       int nseq, int T, int s_inner, long long outer_stride, long long inner_stride,
                       long long t_stride) {
-  __shared__ __align__(16) float hs[4][32];     // per-warp broadcast buffer for the hidden state
+  __shared__ __align__(16) float hs[4][2][32];   // per-warp broadcast buffers for the two hidden states
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int dir = (int)(gw & 1);
-  const long long seq = gw >> 1;
-  if (seq >= nseq) return;
-  const long long base = (seq / s_inner) * outer_stride + (seq % s_inner) * inner_stride;
+  const long long seq0 = (gw >> 1) * 2;
+  if (seq0 >= nseq) return;
+  const bool two = seq0 + 1 < nseq;
+  const long long seq1 = two ? seq0 + 1 : seq0;
+  const long long base[2] = {(seq0 / s_inner) * outer_stride + (seq0 % s_inner) * inner_stride,
+                             (seq1 / s_inner) * outer_stride + (seq1 % s_inner) * inner_stride};
 
   float wr[32], wz[32], wn[32];
   const float* W = Whh + dir * 96 * 32;
@@ -48,168 +53,192 @@ gru32_scan_fwd_kernel(const float* __restrict__ GI, const float* __restrict__ Wh
   }
   const float br = bhh[dir * 96 + lane], bz = bhh[dir * 96 + 32 + lane], bn = bhh[dir * 96 + 64 + lane];
 
-  float h = 0.f;
-  long long row = base + (dir == 0 ? 0 : (long long)(T - 1)) * t_stride;
+  float h[2] = {0.f, 0.f};
+  long long off = (dir == 0 ? 0 : (long long)(T - 1)) * t_stride;     // row offset shared by both sequences
   const long long step_stride = dir == 0 ? t_stride : -t_stride;
-  // The recurrence is a dependent chain of ~500 cycles per step while the GI row of a step comes from
-  // L2/HBM (~1000+ cycles): keep a ring of PF steps of input projections in flight.
-  constexpr int PF = 6;
-  float pr[PF], pz[PF], pn[PF];
+  constexpr int PF = 4;
+  float pr[2][PF], pz[2][PF], pn[2][PF];
 #pragma unroll
-  for (int j = 0; j < PF; ++j) {
-    pr[j] = pz[j] = pn[j] = 0.f;
-    if (j < T) {
-      const float* gp = GI + (row + j * step_stride) * 192 + dir * 96 + lane;
-      pr[j] = gp[0];
-      pz[j] = gp[32];
-      pn[j] = gp[64];
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      pr[u][j] = pz[u][j] = pn[u][j] = 0.f;
+      if (j < T) {
+        const float* gp = GI + (base[u] + off + j * step_stride) * 192 + dir * 96 + lane;
+        pr[u][j] = gp[0];
+        pz[u][j] = gp[32];
+        pn[u][j] = gp[64];
+      }
     }
-  }
   for (int s0 = 0; s0 < T; s0 += PF) {
 #pragma unroll
     for (int j = 0; j < PF; ++j) {
       const int s = s0 + j;
       if (s < T) {
-        const float gr = pr[j], gz = pz[j], gn = pn[j];
-        if (s + PF < T) {
-          const float* np = GI + (row + PF * step_stride) * 192 + dir * 96 + lane;
-          pr[j] = np[0];
-          pz[j] = np[32];
-          pn[j] = np[64];
+        float gr[2], gz[2], gn[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          gr[u] = pr[u][j];
+          gz[u] = pz[u][j];
+          gn[u] = pn[u][j];
+          if (s + PF < T) {
+            const float* np = GI + (base[u] + off + PF * step_stride) * 192 + dir * 96 + lane;
+            pr[u][j] = np[0];
+            pz[u][j] = np[32];
+            pn[u][j] = np[64];
+          }
         }
-        float ar = br, az = bz, an = bn;
-        float ar2 = 0.f, az2 = 0.f, an2 = 0.f;          // two partial chains halve the FMA dependency depth
-        // broadcast h through shared memory: 1 STS + 8 LDS.128 instead of 32 shuffles
         __syncwarp();
-        hs[wib][lane] = h;
+        hs[wib][0][lane] = h[0];
+        hs[wib][1][lane] = h[1];
         __syncwarp();
+        float ar[2] = {br, br}, az[2] = {bz, bz}, an[2] = {bn, bn};
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 hv = *reinterpret_cast<const float4*>(&hs[wib][k4 * 4]);
-          ar = fmaf(wr[k4 * 4 + 0], hv.x, ar);
-          az = fmaf(wz[k4 * 4 + 0], hv.x, az);
-          an = fmaf(wn[k4 * 4 + 0], hv.x, an);
-          ar2 = fmaf(wr[k4 * 4 + 1], hv.y, ar2);
-          az2 = fmaf(wz[k4 * 4 + 1], hv.y, az2);
-          an2 = fmaf(wn[k4 * 4 + 1], hv.y, an2);
-          ar = fmaf(wr[k4 * 4 + 2], hv.z, ar);
-          az = fmaf(wz[k4 * 4 + 2], hv.z, az);
-          an = fmaf(wn[k4 * 4 + 2], hv.z, an);
-          ar2 = fmaf(wr[k4 * 4 + 3], hv.w, ar2);
-          az2 = fmaf(wz[k4 * 4 + 3], hv.w, az2);
-          an2 = fmaf(wn[k4 * 4 + 3], hv.w, an2);
+          const float4 a = *reinterpret_cast<const float4*>(&hs[wib][0][k4 * 4]);
+          const float4 b = *reinterpret_cast<const float4*>(&hs[wib][1][k4 * 4]);
+          const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            ar[0] = fmaf(wr[k4 * 4 + e], av[e], ar[0]);
+            az[0] = fmaf(wz[k4 * 4 + e], av[e], az[0]);
+            an[0] = fmaf(wn[k4 * 4 + e], av[e], an[0]);
+            ar[1] = fmaf(wr[k4 * 4 + e], bv[e], ar[1]);
+            az[1] = fmaf(wz[k4 * 4 + e], bv[e], az[1]);
+            an[1] = fmaf(wn[k4 * 4 + e], bv[e], an[1]);
+          }
         }
-        ar += ar2;
-        az += az2;
-        an += an2;
-        float r = fsigmoid(gr + ar);
-        float z = fsigmoid(gz + az);
-        float n = ftanh(gn + r * an);
-        float hn = n + z * (h - n);
-        OUT[row * 64 + dir * 32 + lane] = hn;
-        if (GATES) {
-          float* g = GATES + row * 320 + dir * 160 + lane;
-          g[0] = r;
-          g[32] = z;
-          g[64] = n;
-          g[96] = an;
-          g[128] = h;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float r = fsigmoid(gr[u] + ar[u]);
+          float z = fsigmoid(gz[u] + az[u]);
+          float n = ftanh(gn[u] + r * an[u]);
+          float hn = n + z * (h[u] - n);
+          if (u == 0 || two) {
+            const long long row = base[u] + off;
+            OUT[row * 64 + dir * 32 + lane] = hn;
+            if (GATES) {
+              float* g = GATES + row * 320 + dir * 160 + lane;
+              g[0] = r;
+              g[32] = z;
+              g[64] = n;
+              g[96] = an[u];
+              g[128] = h[u];
+            }
+          }
+          h[u] = hn;
         }
-        h = hn;
-        row += step_stride;
+        off += step_stride;
       }
     }
   }
 }
 
-// dGI [rows][192] (grad wrt the input projections), dGH [rows][192] (grad wrt W_hh h + b_hh)
+// dGI [rows][192] (grad wrt the input projections), dGH [rows][192] (grad wrt W_hh h + b_hh); two sequences per warp
 __global__ void __launch_bounds__(128)
 gru32_scan_bwd_kernel(const float* __restrict__ dOUT, const float* __restrict__ GATES,
                       const float* __restrict__ Whh, float* __restrict__ dGI, float* __restrict__ dGH, int nseq,
                       int T, int s_inner, long long outer_stride, long long inner_stride, long long t_stride) {
-  __shared__ __align__(16) float gs[4][96];     // per-warp broadcast buffer: dpr | dpz | dhn
+  __shared__ __align__(16) float gs[4][2][96];   // per-warp broadcast buffers: dpr | dpz | dhn of both sequences
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int dir = (int)(gw & 1);
-  const long long seq = gw >> 1;
-  if (seq >= nseq) return;
-  const long long base = (seq / s_inner) * outer_stride + (seq % s_inner) * inner_stride;
+  const long long seq0 = (gw >> 1) * 2;
+  if (seq0 >= nseq) return;
+  const bool two = seq0 + 1 < nseq;
+  const long long seq1 = two ? seq0 + 1 : seq0;
+  const long long base[2] = {(seq0 / s_inner) * outer_stride + (seq0 % s_inner) * inner_stride,
+                             (seq1 / s_inner) * outer_stride + (seq1 % s_inner) * inner_stride};
 
   float wc[96];  // column `lane` of W_hh[dir]
   const float* W = Whh + dir * 96 * 32;
 #pragma unroll
   for (int i = 0; i < 96; ++i) wc[i] = W[i * 32 + lane];
 
-  float dh = 0.f;
-  // walk the recurrence backwards: last processed step first
-  long long row = base + (dir == 0 ? (long long)(T - 1) : 0) * t_stride;
+  float dh[2] = {0.f, 0.f};
+  long long off = (dir == 0 ? (long long)(T - 1) : 0) * t_stride;   // walk the recurrence backwards
   const long long step_stride = dir == 0 ? -t_stride : t_stride;
-  constexpr int PF = 4;
-  float qr[PF], qz[PF], qn[PF], qg[PF], qh[PF], qo[PF];
+  constexpr int PF = 2;
+  float qr[2][PF], qz[2][PF], qn[2][PF], qg[2][PF], qh[2][PF], qo[2][PF];
 #pragma unroll
-  for (int j = 0; j < PF; ++j) {
-    qr[j] = qz[j] = qn[j] = qg[j] = qh[j] = qo[j] = 0.f;
-    if (j < T) {
-      const long long rj = row + j * step_stride;
-      const float* g = GATES + rj * 320 + dir * 160 + lane;
-      qr[j] = g[0]; qz[j] = g[32]; qn[j] = g[64]; qg[j] = g[96]; qh[j] = g[128];
-      qo[j] = dOUT[rj * 64 + dir * 32 + lane];
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      qr[u][j] = qz[u][j] = qn[u][j] = qg[u][j] = qh[u][j] = qo[u][j] = 0.f;
+      if (j < T) {
+        const long long rj = base[u] + off + j * step_stride;
+        const float* g = GATES + rj * 320 + dir * 160 + lane;
+        qr[u][j] = g[0]; qz[u][j] = g[32]; qn[u][j] = g[64]; qg[u][j] = g[96]; qh[u][j] = g[128];
+        qo[u][j] = dOUT[rj * 64 + dir * 32 + lane];
+      }
     }
-  }
   for (int s0 = 0; s0 < T; s0 += PF) {
 #pragma unroll
     for (int j = 0; j < PF; ++j) {
       const int s = s0 + j;
       if (s < T) {
-        const float r = qr[j], z = qz[j], n = qn[j], ghn = qg[j], hp = qh[j];
-        const float go = qo[j] + dh;
-        if (s + PF < T) {
-          const long long rj = row + PF * step_stride;
-          const float* g = GATES + rj * 320 + dir * 160 + lane;
-          qr[j] = g[0]; qz[j] = g[32]; qn[j] = g[64]; qg[j] = g[96]; qh[j] = g[128];
-          qo[j] = dOUT[rj * 64 + dir * 32 + lane];
-        }
-        float dn = go * (1.f - z);
-        float dz = go * (hp - n);
-        float dpn = dn * (1.f - n * n);
-        float dpr = dpn * ghn * r * (1.f - r);
-        float dpz = dz * z * (1.f - z);
-        float dhn = dpn * r;
-        float* o = dGI + row * 192 + dir * 96 + lane;
-        o[0] = dpr;
-        o[32] = dpz;
-        o[64] = dpn;
-        float* o2 = dGH + row * 192 + dir * 96 + lane;
-        o2[0] = dpr;
-        o2[32] = dpz;
-        o2[64] = dhn;
-        float acc = go * z, acc2 = 0.f, acc3 = 0.f;
-        __syncwarp();
-        gs[wib][lane] = dpr;
-        gs[wib][32 + lane] = dpz;
-        gs[wib][64 + lane] = dhn;
+        float gz_[2], go_[2];
         __syncwarp();
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 a = *reinterpret_cast<const float4*>(&gs[wib][k4 * 4]);
-          const float4 b = *reinterpret_cast<const float4*>(&gs[wib][32 + k4 * 4]);
-          const float4 c = *reinterpret_cast<const float4*>(&gs[wib][64 + k4 * 4]);
-          acc = fmaf(wc[k4 * 4 + 0], a.x, acc);
-          acc2 = fmaf(wc[32 + k4 * 4 + 0], b.x, acc2);
-          acc3 = fmaf(wc[64 + k4 * 4 + 0], c.x, acc3);
-          acc = fmaf(wc[k4 * 4 + 1], a.y, acc);
-          acc2 = fmaf(wc[32 + k4 * 4 + 1], b.y, acc2);
-          acc3 = fmaf(wc[64 + k4 * 4 + 1], c.y, acc3);
-          acc = fmaf(wc[k4 * 4 + 2], a.z, acc);
-          acc2 = fmaf(wc[32 + k4 * 4 + 2], b.z, acc2);
-          acc3 = fmaf(wc[64 + k4 * 4 + 2], c.z, acc3);
-          acc = fmaf(wc[k4 * 4 + 3], a.w, acc);
-          acc2 = fmaf(wc[32 + k4 * 4 + 3], b.w, acc2);
-          acc3 = fmaf(wc[64 + k4 * 4 + 3], c.w, acc3);
+        for (int u = 0; u < 2; ++u) {
+          const float r = qr[u][j], z = qz[u][j], n = qn[u][j], ghn = qg[u][j], hp = qh[u][j];
+          const float go = qo[u][j] + dh[u];
+          if (s + PF < T) {
+            const long long rj = base[u] + off + PF * step_stride;
+            const float* g = GATES + rj * 320 + dir * 160 + lane;
+            qr[u][j] = g[0]; qz[u][j] = g[32]; qn[u][j] = g[64]; qg[u][j] = g[96]; qh[u][j] = g[128];
+            qo[u][j] = dOUT[rj * 64 + dir * 32 + lane];
+          }
+          float dn = go * (1.f - z);
+          float dz = go * (hp - n);
+          float dpn = dn * (1.f - n * n);
+          float dpr = dpn * ghn * r * (1.f - r);
+          float dpz = dz * z * (1.f - z);
+          float dhn = dpn * r;
+          if (u == 0 || two) {
+            const long long row = base[u] + off;
+            float* o = dGI + row * 192 + dir * 96 + lane;
+            o[0] = dpr;
+            o[32] = dpz;
+            o[64] = dpn;
+            float* o2 = dGH + row * 192 + dir * 96 + lane;
+            o2[0] = dpr;
+            o2[32] = dpz;
+            o2[64] = dhn;
+          }
+          gs[wib][u][lane] = dpr;
+          gs[wib][u][32 + lane] = dpz;
+          gs[wib][u][64 + lane] = dhn;
+          gz_[u] = z;
+          go_[u] = go;
         }
-        dh = acc + acc2 + acc3;
-        row += step_stride;
+        __syncwarp();
+        float acc[2] = {go_[0] * gz_[0], go_[1] * gz_[1]}, acc2[2] = {0.f, 0.f}, acc3[2] = {0.f, 0.f};
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 a = *reinterpret_cast<const float4*>(&gs[wib][u][k4 * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&gs[wib][u][32 + k4 * 4]);
+            const float4 c = *reinterpret_cast<const float4*>(&gs[wib][u][64 + k4 * 4]);
+            acc[u] = fmaf(wc[k4 * 4 + 0], a.x, acc[u]);
+            acc2[u] = fmaf(wc[32 + k4 * 4 + 0], b.x, acc2[u]);
+            acc3[u] = fmaf(wc[64 + k4 * 4 + 0], c.x, acc3[u]);
+            acc[u] = fmaf(wc[k4 * 4 + 1], a.y, acc[u]);
+            acc2[u] = fmaf(wc[32 + k4 * 4 + 1], b.y, acc2[u]);
+            acc3[u] = fmaf(wc[64 + k4 * 4 + 1], c.y, acc3[u]);
+            acc[u] = fmaf(wc[k4 * 4 + 2], a.z, acc[u]);
+            acc2[u] = fmaf(wc[32 + k4 * 4 + 2], b.z, acc2[u]);
+            acc3[u] = fmaf(wc[64 + k4 * 4 + 2], c.z, acc3[u]);
+            acc[u] = fmaf(wc[k4 * 4 + 3], a.w, acc[u]);
+            acc2[u] = fmaf(wc[32 + k4 * 4 + 3], b.w, acc2[u]);
+            acc3[u] = fmaf(wc[64 + k4 * 4 + 3], c.w, acc3[u]);
+          }
+        }
+        dh[0] = acc[0] + acc2[0] + acc3[0];
+        dh[1] = acc[1] + acc2[1] + acc3[1];
+        off += step_stride;
       }
     }
   }
@@ -336,7 +365,7 @@ int tatt_gru32_scan_fwd(const float* GI, const float* Whh, const float* bhh, flo
                         void* stream) {
   if (nseq <= 0 || T <= 0) return 0;
   TATT_REQUIRE(s_inner >= 1, "gru32_scan_fwd: s_inner must be >= 1");
-  long long warps = 2LL * nseq;
+  long long warps = 2LL * ((nseq + 1) / 2);
   int blocks = (int)((warps + 3) / 4);
   gru32_scan_fwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(GI, Whh, bhh, OUT, GATES, nseq, T, s_inner,
                                                                   outer_stride, inner_stride, t_stride);
@@ -349,7 +378,7 @@ int tatt_gru32_scan_bwd(const float* dOUT, const float* GATES, const float* Whh,
                         void* stream) {
   if (nseq <= 0 || T <= 0) return 0;
   TATT_REQUIRE(s_inner >= 1, "gru32_scan_bwd: s_inner must be >= 1");
-  long long warps = 2LL * nseq;
+  long long warps = 2LL * ((nseq + 1) / 2);
   int blocks = (int)((warps + 3) / 4);
   gru32_scan_bwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(dOUT, GATES, Whh, dGI, dGH, nseq, T, s_inner,
                                                                   outer_stride, inner_stride, t_stride);
