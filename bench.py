@@ -27,6 +27,7 @@ import torch  # noqa: E402
 
 METRIC = "SR images/sec (32x128 LR, fwd+bwd)"
 UNIT = "images/s"
+NCU_CONV_TRAFFIC_BYTES = 178.2e6         # split pass 91.1 MB + conv3x3_tma_kernel 87.1 MB (profiles/r1_ncu_full_tc*_conv3x3*.csv)
 ALG_FLOPS_FWD_BWD_G32 = 3.0 * 9.33e9     # ~9.33 GFLOP/img forward (RPE input-proj hoisted) x3 for fwd+bwd
 
 
@@ -126,9 +127,11 @@ def run_reference(args):
 
 
 def conv_roofline(dev, batch, h, w, peaks):
-    """Dominant kernel = the 3x3 64->64 implicit-GEMM convolution (11 forward instances per image plus their
-    data/weight gradients).  Algorithmic FLOPs per launch = 2*pixels*64*576; timed alone with CUDA events."""
-    from tatt_b200 import ops
+    """Dominant kernel = the 3x3 64->64 implicit-GEMM convolution on tcgen05 (11 forward instances per image plus
+    their data/weight gradients).  One "launch" = the operand split pass + tc2_gemm_kernel<IM2COL_K> of one conv.
+    Algorithmic FLOPs per launch = 2 * pixels * 64 * 576 (SURVEY 8d conv figure x pixels); timed alone with CUDA
+    events on the launching stream, L2 flushed (256 MB write) between launches."""
+    from tatt_b200 import _cabi, ops
     x = torch.randn(batch, h, w, 64, device=dev)
     wt = torch.randn(64, 64, 3, 3, device=dev) * 0.05
     b = torch.zeros(64, device=dev)
@@ -143,7 +146,6 @@ def conv_roofline(dev, batch, h, w, peaks):
         wtp = ops.conv_pack(wt, 64, 64, False)
         y = torch.empty_like(x)
         e0.record()
-        from tatt_b200 import _cabi
         _cabi.call("tatt_conv2d_igemm", x.data_ptr(), wtp.data_ptr(), b.data_ptr(), y.data_ptr(), batch, h, w, 64, 64,
                    3, 3, 1, 1, 0, ws.data_ptr(), wsb, ops._stream())
         e1.record()
@@ -152,11 +154,15 @@ def conv_roofline(dev, batch, h, w, peaks):
     t = sum(ts) / len(ts)
     flops = 2.0 * batch * h * w * 64 * 576
     peak = peaks.get("bf16_tflops", 1590.0)
-    return {"bound": "tensor", "kernel": "gemm_kernel<128,64,16,8,4,IM2COL,KN> (conv3x3 64->64, fp32 FFMA)",
+    # dram__bytes_read.sum + dram__bytes_write.sum of split + GEMM kernels from the committed ncu --set full capture
+    # (profiles/r1_ncu_full_tc2_conv3x3.csv), same shape; algorithmic bytes = 67 MB in + 67 MB out
+    traffic = NCU_CONV_TRAFFIC_BYTES if (batch, h, w) == (64, 32, 128) else None
+    return {"bound": "tensor", "kernel": "split_dense_kernel + conv3x3_tma_kernel<2> (conv3x3 64->64, NHWC; TMA halo tile "
+            "+ TMA weight ring, tcgen05 kind::f16 with a bf16 hi/lo operand split, 3 MMAs per k-step, fp32 TMEM accumulators)",
             "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak,
-            "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks
-            else "fallback 1.59 PFLOP/s", "launch_ms": t * 1e3,
-            "note": "fp32 CUDA-core kernel measured against the bf16 tensor-core peak"}
+            "traffic": traffic, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if "bf16_tflops" in peaks
+            else "fallback 1.59 PFLOP/s, of fallback", "launch_ms": t * 1e3, "algorithmic_flops_per_launch": flops,
+            "note": "fp32-parity mode costs 3 bf16 MMAs per product, so the ceiling of this kernel is 1/3 of the bf16 peak"}
 
 
 def run_ours(args):

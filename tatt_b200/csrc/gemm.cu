@@ -706,6 +706,11 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
                       void* stream) {
   TATT_REQUIRE(Cin % 4 == 0, "conv2d_igemm: Cin (%d) must be a multiple of 4 (pad channels)", Cin);
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv2d_igemm: too many pixels");
+  if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout == 64 && ws &&
+      !(flags & (F_ACCUM | F_RELU | F_FP32))) {
+    int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, ws, ws_bytes, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   GemmP p = {};
   p.A = X; p.B = Wt; p.C = Y; p.bias = bias;
   p.M = nimg * H * W; p.N = Cout; p.K = KH * KW * Cin;

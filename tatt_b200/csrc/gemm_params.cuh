@@ -58,3 +58,7 @@ int tatt_tc2_split(const float* src, long long ld, long long rows, int cols, int
 // v2 (tc2_gemm.cu): operands pre-split into bf16 planes in `ws`; same return convention
 int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* ws, long long ws_bytes,
                          cudaStream_t st);
+
+// TMA + halo-reuse kernel for the 3x3 / 64->64 convolution (tc3_conv.cu); same return convention
+int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
+                            void* ws, long long ws_bytes, cudaStream_t st);

@@ -1,0 +1,293 @@
+// 3x3 / 64->64 convolution (stride 1, pad 1, NHWC) on tcgen05 with TMA-staged halo tiles.
+//
+// The implicit-GEMM kernels of tc2_gemm.cu re-read the activation tile once per tap (9x) and the weight tile once
+// per CTA per tap: 885 MB of L2->SMEM traffic per conv at the bench shape, which bounds them (ncu: tensor pipe 25 %,
+// profiles/r1_ncu_full_tc2_conv3x3.csv).  Here one CTA owns R output rows x 128 output columns of one image:
+//   * ONE TMA box load per bf16 plane (hi, lo) brings the (R+2) x 130 pixel halo x 64 channels into shared memory
+//     (out-of-image coordinates are zero-filled by the TMA unit = the conv padding), 128B-swizzled;
+//   * the A operand of tap (dy,dx) for output row r is simply the 128 consecutive halo pixels starting at
+//     (r+dy+1)*130 + (dx+1): a shifted UMMA descriptor into the same tile -- no re-load, no im2col address math;
+//   * the 9 weight taps ([64 co][64 ci] bf16 hi+lo = 16 KB each) stream through a 3-stage TMA ring;
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (3 MMAs per k-step: lo*hi, hi*lo,
+//     hi*hi into fp32 TMEM accumulators, one 64-column accumulator per output row), warps 2-5 = epilogue
+//     (tcgen05.ld -> +bias -> HBM).
+// L2->SMEM traffic per conv drops ~3x (A: (R+2)/R reads per pixel instead of 9; weights once per R rows).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "gemm_params.cuh"
+
+namespace {
+
+constexpr int TW = 128;        // output columns per CTA
+constexpr int HALO_W = TW + 2;
+constexpr int NSTAGE = 5;      // weight-tap ring (5 x 16 KB: load latency hidden behind 4 taps of MMAs)
+constexpr int B_TAP_BYTES = 2 * 64 * 128;   // hi + lo
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major SWIZZLE_128B descriptor; `base_off` = (start >> 7) & 7 when the start is not on a 1024-byte boundary
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t base_off) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int R>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                   float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int base_off_mode) {
+  constexpr int A_ROWS = (R + 2) * HALO_W;
+  constexpr int A_PLANE = ((A_ROWS * 128 + 1023) / 1024) * 1024;
+  constexpr int TMEM_COLS = (R * 64 <= 64) ? 64 : ((R * 64 <= 128) ? 128 : 256);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long bar_a, bar_done, bar_full[NSTAGE], bar_empty[NSTAGE];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nxt = W / TW, nyb = H / R;
+  const int xb = blockIdx.x % nxt;
+  const int yb = (blockIdx.x / nxt) % nyb;
+  const int n = blockIdx.x / (nxt * nyb);
+  const int x0 = xb * TW, y0 = yb * R;
+  const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + A_PLANE, b_ring = a_lo + A_PLANE;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_a), 1);
+    mbar_init(smem_u32(&bar_done), 1);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&bar_a), 2u * (uint32_t)(A_ROWS * 128));
+      tma_load_4d(a_hi, &tmAh, smem_u32(&bar_a), 0, x0 - 1, y0 - 1, n);
+      tma_load_4d(a_lo, &tmAl, smem_u32(&bar_a), 0, x0 - 1, y0 - 1, n);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int s = tap % NSTAGE;
+        if (tap >= NSTAGE) mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((tap / NSTAGE) - 1) & 1));
+        const uint32_t dst = b_ring + (uint32_t)(s * B_TAP_BYTES);
+        mbar_expect_tx(smem_u32(&bar_full[s]), (uint32_t)B_TAP_BYTES);
+        tma_load_2d(dst, &tmBh, smem_u32(&bar_full[s]), tap * 64, 0);
+        tma_load_2d(dst + 64 * 128, &tmBl, smem_u32(&bar_full[s]), tap * 64, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(smem_u32(&bar_a), 0);
+      tc_fence_after();
+      for (int tap = 0; tap < 9; ++tap) {
+        const int s = tap % NSTAGE;
+        mbar_wait(smem_u32(&bar_full[s]), (uint32_t)((tap / NSTAGE) & 1));
+        tc_fence_after();
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const uint32_t b_hi = b_ring + (uint32_t)(s * B_TAP_BYTES), b_lo = b_hi + 64 * 128;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint32_t row0 = (uint32_t)((r + dy + 1) * HALO_W + (dx + 1)) * 128u;
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint32_t ko = k16 * 32;
+            const uint32_t sa_h = a_hi + row0 + ko, sa_l = a_lo + row0 + ko;
+            const uint32_t bo_h = base_off_mode ? ((sa_h >> 7) & 7) : 0, bo_l = base_off_mode ? ((sa_l >> 7) & 7) : 0;
+            const uint64_t dah = make_desc(sa_h, bo_h), dal = make_desc(sa_l, bo_l);
+            const uint64_t dbh = make_desc(b_hi + ko, 0), dbl = make_desc(b_lo + ko, 0);
+            const uint32_t tm = tmem_base + (uint32_t)(r * 64);
+            umma_bf16(tm, dal, dbh, idesc, (tap > 0 || k16 > 0) ? 1u : 0u);
+            umma_bf16(tm, dah, dbl, idesc, 1u);
+            umma_bf16(tm, dah, dbh, idesc, 1u);
+          }
+        }
+        umma_commit(smem_u32(&bar_empty[s]));
+      }
+      umma_commit(smem_u32(&bar_done));
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
+    mbar_wait(smem_u32(&bar_done), 0);
+    tc_fence_after();
+    const int lg = warp & 3;
+    const int px = x0 + lg * 32 + lane;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float* dst = Y + (((long long)n * H + (y0 + r)) * W + px) * 64;
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(r * 64 + c16 * 16), v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 o;
+          o.x = __uint_as_float(v[4 * q + 0]);
+          o.y = __uint_as_float(v[4 * q + 1]);
+          o.z = __uint_as_float(v[4 * q + 2]);
+          o.w = __uint_as_float(v[4 * q + 3]);
+          if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c16 * 16 + 4 * q));
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          }
+          *reinterpret_cast<float4*>(dst + c16 * 16 + 4 * q) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+static inline long long rup8(long long x) { return (x + 7) & ~7LL; }
+
+}  // namespace
+
+// conv3x3 64->64 through the TMA kernel.  Returns 0 ok, 1 error, -1 not eligible (caller falls through).
+int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
+                            void* ws, long long ws_bytes, cudaStream_t st) {
+  static const int mode = []() {          // TATT_TMA: 0 = off, 1 = on (base_offset 0), 2 = on (base_offset from address)
+    const char* e = getenv("TATT_TMA");
+    return e ? atoi(e) : 1;
+  }();
+  if (mode == 0 || ws == nullptr || W % TW != 0 || H % 2 != 0) return -1;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  const long long P = (long long)nimg * H * W;
+  const long long nA = rup8(P * 64), nB = rup8(64LL * 576);
+  if ((long long)sizeof(__nv_bfloat16) * 2 * (nA + nB) > ws_bytes || (((uintptr_t)ws) & 15)) return -1;
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16 *Ahi = base, *Alo = base + nA, *Bhi = base + 2 * nA, *Blo = base + 2 * nA + nB;
+  int rc = tatt_tc2_split(X, 64, P, 64, 0, Ahi, Alo, nullptr, st);          // activations -> [P][64] planes
+  if (rc) return rc;
+  rc = tatt_tc2_split(Wt, 64, 576, 64, 1, Bhi, Blo, nullptr, st);            // Wt[576][64] -> planes [64 co][576 k]
+  if (rc) return rc;
+
+  constexpr int R = 2;
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  {
+    cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+    cuuint32_t box[4] = {64, HALO_W, R + 2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int pl = 0; pl < 2; ++pl) {
+      CUresult r = enc(pl ? &tmAl : &tmAh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, pl ? (void*)Alo : (void*)Ahi, gdim, gstr,
+                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return tatt_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+    }
+  }
+  {
+    cuuint64_t gdim[2] = {576, 64};
+    cuuint64_t gstr[1] = {576 * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    for (int pl = 0; pl < 2; ++pl) {
+      CUresult r = enc(pl ? &tmBl : &tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pl ? (void*)Blo : (void*)Bhi, gdim, gstr,
+                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return tatt_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    }
+  }
+  constexpr int A_PLANE = ((((R + 2) * HALO_W) * 128 + 1023) / 1024) * 1024;
+  const int smem = 2 * A_PLANE + NSTAGE * B_TAP_BYTES + 1024;
+  TATT_CUDA(cudaFuncSetAttribute(conv3x3_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = nimg * (H / R) * (W / TW);
+  conv3x3_tma_kernel<R><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, mode == 2 ? 1 : 0);
+  TATT_LAUNCH_CHECK("conv3x3_tma_kernel");
+  return 0;
+}

@@ -63,7 +63,8 @@ def test_gemm_batched_strided():
 # ------------------------------------------------------------------------------------------ conv
 @pytest.mark.parametrize("N,H,W,Cin,Cout,k", [(2, 16, 64, 64, 64, 3), (3, 8, 16, 4, 64, 9), (2, 12, 20, 64, 4, 9),
                                              (2, 16, 64, 64, 256, 3), (2, 6, 10, 4, 32, 3), (2, 2, 8, 128, 256, 3),
-                                             (1, 1, 2, 256, 256, 3), (2, 8, 8, 3, 64, 9), (2, 8, 8, 64, 3, 9)])
+                                             (1, 1, 2, 256, 256, 3), (2, 8, 8, 3, 64, 9), (2, 8, 8, 64, 3, 9),
+                                             (2, 4, 128, 64, 64, 3), (1, 6, 256, 64, 64, 3)])   # last two: TMA halo kernel
 def test_conv2d_fwd_bwd(N, H, W, Cin, Cout, k):
     from tatt_b200 import ops
     pad = k // 2
