@@ -510,7 +510,14 @@ static int launch_kind(const Tc2P& q, cudaStream_t st) {
     const char* e = getenv("TATT_TC2_STAGES");
     return (e && e[0] == '4') ? 4 : 2;
   }();
-  if (stages == 4) return launch_kind_s<KIND, 4>(q, st);
+  // weight-gradient kinds stream 27-68 k-tiles per CTA: deeper pipeline (TATT_TC2_STAGES_MN=2 to disable)
+  static const int stages_mn = []() {
+    const char* e = getenv("TATT_TC2_STAGES_MN");
+    return (e && e[0] == '2') ? 2 : 4;
+  }();
+  constexpr bool kMN = (KIND == K2_DENSE_MN || KIND == K2_IM2COL_MN);
+  const bool long_k = (KIND == K2_DENSE_K) && (q.kper / BK >= 12);      // e.g. the RPE recurrent GEMMs
+  if (((kMN || long_k) ? stages_mn : stages) == 4) return launch_kind_s<KIND, 4>(q, st);
   return launch_kind_s<KIND, 2>(q, st);
 }
 
