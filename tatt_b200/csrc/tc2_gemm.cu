@@ -408,16 +408,22 @@ __global__ void split_dense_kernel(const float* __restrict__ src, long long ld, 
     *reinterpret_cast<uint2*>(lo + r * colsP + c) = lv;
   }
 }
-// same split, plus out[c] += sum_r src[r][c] (the bias gradient) -- block = (colsP/4) x R threads
+// same split, plus out[c] += sum_r src[r][c] (the bias gradient).  blockDim.x is a multiple of colsP/4, so every
+// thread keeps the same 4 columns while it grid-strides over rows: partial sums stay in registers.
 __global__ void split_colsum_kernel(const float* __restrict__ src, long long ld, long long rows, int cols, int colsP,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    float* __restrict__ colsum, int rows_per_block, int vec) {
-  extern __shared__ float red[];          // [blockDim.y][colsP]
-  const int c = threadIdx.x * 4;
-  long long r0 = (long long)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
-  if (r1 > rows) r1 = rows;
+                                    float* __restrict__ colsum, int vec) {
+  extern __shared__ float red[];          // [colsP]
+  const int tx = colsP / 4;
+  const int cg = threadIdx.x % tx;
+  const int c = cg * 4;
+  const long long rstep = ((long long)gridDim.x * blockDim.x) / tx;
+  long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / tx;
+  for (int i = threadIdx.x; i < colsP; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
   float a[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+#pragma unroll 4
+  for (; r < rows; r += rstep) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     const float* s = src + r * ld + c;
     if (vec && c + 3 < cols) {
@@ -443,16 +449,9 @@ __global__ void split_colsum_kernel(const float* __restrict__ src, long long ld,
     *reinterpret_cast<uint2*>(lo + r * colsP + c) = lv;
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) red[threadIdx.y * colsP + c + j] = a[j];
+  for (int j = 0; j < 4; ++j) atomicAdd(&red[c + j], a[j]);
   __syncthreads();
-  if (threadIdx.y == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float t = 0.f;
-      for (int y = 0; y < (int)blockDim.y; ++y) t += red[y * colsP + c + j];
-      if (c + j < cols) atomicAdd(colsum + c + j, t);
-    }
-  }
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) atomicAdd(colsum + i, red[i]);
 }
 // src [K][N] (row stride ld) -> planes [N][Kp]   (small weight matrices)
 __global__ void split_transpose_kernel(const float* __restrict__ src, long long ld, int K, int N, int Kp,
@@ -532,14 +531,14 @@ int tatt_tc2_split(const float* src, long long ld, long long rows, int cols, int
     TATT_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * cols, st));
     if (rows <= 0) return 0;
     const int tx = colsP / 4;
-    int ty = 256 / tx;
-    if (ty < 1) ty = 1;
-    int rpb = 256;
-    if (rows > 256LL * 148 * 8) rpb = (int)((rows + 148 * 8 - 1) / (148 * 8));
-    int blocks = (int)((rows + rpb - 1) / rpb);
+    int nthr = (256 / tx) * tx;
+    if (nthr < tx) nthr = tx;
+    long long want = (rows * tx + nthr - 1) / nthr;
+    int blocks = (int)(want < 148LL * 8 ? want : 148LL * 8);
+    if (blocks < 1) blocks = 1;
     int vec = (ld % 4 == 0 && aligned16(src)) ? 1 : 0;
-    split_colsum_kernel<<<blocks, dim3(tx, ty), sizeof(float) * ty * colsP, st>>>(
-        src, ld, rows, cols, colsP, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, colsum, rpb, vec);
+    split_colsum_kernel<<<blocks, nthr, sizeof(float) * colsP, st>>>(src, ld, rows, cols, colsP, (__nv_bfloat16*)hi,
+                                                                   (__nv_bfloat16*)lo, colsum, vec);
     TATT_LAUNCH_CHECK("split_colsum_kernel");
     return 0;
   }
