@@ -42,15 +42,26 @@ __device__ __forceinline__ float warp_max(float v) {
 // activation codes shared by several kernels
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_MISH = 2 };
 
-__device__ __forceinline__ float softplus_t(float x) {  // torch softplus, beta 1, threshold 20
-  return x > 20.f ? x : log1pf(expf(x));
+// mish(x) = x * tanh(softplus(x)) (model/tsrn.py:1061-1064, torch softplus threshold 20).  With e = e^x:
+// tanh(ln(1+e)) = n / (n + 2), n = e (e + 2)  (no cancellation for very negative x), sigmoid(x) = e / (1 + e):
+// one ex2 and one reciprocal replace tanhf(log1pf(expf(x))) (error ~1e-6; the path's tolerance is 1e-3).
+__device__ __forceinline__ float mish_tanh_sp(float x, float& e_out) {
+  const float e = __expf(fminf(x, 20.f));
+  e_out = e;
+  const float n = e * (e + 2.f);
+  return __fdividef(n, n + 2.f);
 }
-__device__ __forceinline__ float mish_f(float x) { return x * tanhf(softplus_t(x)); }
+__device__ __forceinline__ float mish_f(float x) {
+  float e;
+  const float th = mish_tanh_sp(x, e);
+  return x > 20.f ? x : x * th;
+}
 __device__ __forceinline__ float mish_grad(float x) {
-  float sp = softplus_t(x);
-  float t = tanhf(sp);
-  float sg = x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
-  return t + x * (1.f - t * t) * sg;
+  if (x > 20.f) return 1.f;
+  float e;
+  const float th = mish_tanh_sp(x, e);
+  const float sg = __fdividef(e, 1.f + e);
+  return th + x * (1.f - th * th) * sg;
 }
 __device__ __forceinline__ float act_fwd(float z, int act) {
   if (act == ACT_RELU) return fmaxf(z, 0.f);

@@ -127,20 +127,31 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ X, const float* __
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, int act,
-                                    int training, float invP, long long total, int C, float* __restrict__ dX) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+                                    int training, float invP, long long total4, int C4, float* __restrict__ dX) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    float m = mean[c], is = invstd[c], g = gamma[c];
-    float xh = (X[i] - m) * is;
-    float dz = dY[i];
-    if (act != ACT_NONE) dz *= act_grad(xh * g + beta[c], act);
-    float v;
-    if (training)
-      v = g * is * (dz - dbeta[c] * invP - xh * dgamma[c] * invP);
-    else
-      v = g * is * dz;
-    dX[i] = v;
+    const int c = (int)(i % C4) * 4;
+    const float4 x = reinterpret_cast<const float4*>(X)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(dY)[i];
+    const float4 m = *reinterpret_cast<const float4*>(mean + c);
+    const float4 is = *reinterpret_cast<const float4*>(invstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    const float4 dg = *reinterpret_cast<const float4*>(dgamma + c);
+    const float4 db = *reinterpret_cast<const float4*>(dbeta + c);
+    const float xv[4] = {x.x, x.y, x.z, x.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+    const float mv[4] = {m.x, m.y, m.z, m.w}, iv[4] = {is.x, is.y, is.z, is.w};
+    const float gav[4] = {ga.x, ga.y, ga.z, ga.w}, bev[4] = {be.x, be.y, be.z, be.w};
+    const float dgv[4] = {dg.x, dg.y, dg.z, dg.w}, dbv[4] = {db.x, db.y, db.z, db.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xh = (xv[j] - mv[j]) * iv[j];
+      float dz = gv[j];
+      if (act != ACT_NONE) dz *= act_grad(xh * gav[j] + bev[j], act);
+      o[j] = training ? gav[j] * iv[j] * (dz - dbv[j] * invP - xh * dgv[j] * invP) : gav[j] * iv[j] * dz;
+    }
+    reinterpret_cast<float4*>(dX)[i] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -279,9 +290,10 @@ int tatt_bn_bwd(const float* X, const float* dY, const float* mean, const float*
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)ws, C, dgamma, dbeta);
   TATT_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   if (dX) {
-    long long total = P * C;
-    bn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(X, dY, mean, invstd, gamma, beta, dgamma, dbeta, act,
-                                                          training, 1.f / (float)P, total, C, dX);
+    TATT_REQUIRE(C % 4 == 0, "bn_bwd: C must be a multiple of 4");
+    long long total4 = P * C / 4;
+    bn_bwd_apply_kernel<<<ew_blocks(total4), 256, 0, st>>>(X, dY, mean, invstd, gamma, beta, dgamma, dbeta, act,
+                                                           training, 1.f / (float)P, total4, C / 4, dX);
     TATT_LAUNCH_CHECK("bn_bwd_apply_kernel");
   }
   return 0;
