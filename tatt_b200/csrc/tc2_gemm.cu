@@ -658,8 +658,10 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
   bool split = want_split;
   int sk = 1;
   if (want_split) {
-    long long target = 148LL * 2;
-    sk = (int)((target + tiles - 1) / tiles);
+    // the MN (weight-gradient) kinds run the 4-stage / 1-CTA-per-SM pipeline: aim at exactly one wave
+    long long target = mn ? 148LL : 148LL * 2;
+    sk = (int)(target / tiles);
+    if (sk < 1) sk = 1;
     int maxsk = ceil_div(p.K, BK * 4);
     if (sk > maxsk) sk = maxsk;
   } else if (tiles < 74 && p.K >= 512 && !(q.flags & F_RELU)) {

@@ -229,3 +229,36 @@ def test_graphed_trainer_matches_eager_trainer():
     assert ge.shape == gg.shape
     rel = ((ge - gg).norm() / ge.norm()).item()
     assert rel <= 1e-3, "graph replay vs eager gradient rel-L2 %.3e" % rel
+
+
+def test_config1_single_crop_psnr_vs_reference_math():
+    """BASELINE configs[0]: one 32x128 -> 64x256 crop, eval forward; PSNR (utils/ssim_psnr.py:9-15 formula) of our SR
+    output against the reference's CPU output.  Identical images give +inf; fp32-level agreement is > 100 dB."""
+    import tatt_b200
+    from oracle import ref_harness as rh
+    from oracle import tatt_oracle as orc
+    torch.manual_seed(gu.SEED)
+    net = tatt_b200.TSRN_TL_TRANS(scale_factor=2, width=256, height=64, STN=False, mask=True)
+    rh.perturb_(net)
+    net.eval()
+    sd = orc.clone_sd(net.state_dict())
+    x, tp = orc.synthetic_inputs(1, 32, 128, seed=gu.SEED)
+    ref, ref_w, _ = orc.tsrn_tl_trans_forward(sd, x, tp, training=False)
+    with torch.no_grad():
+        out, w = net.to(DEV)(x.to(DEV), tp.to(DEV))
+    assert out.shape == (1, 4, 64, 256) and w.shape == (1, 32 * 128, 26)
+    psnr = orc.psnr(out.cpu(), ref)
+    print("config-1 PSNR new-vs-reference: %.1f dB" % psnr)
+    assert psnr > 100.0
+
+
+def test_config5_two_geometry_buckets_in_one_process():
+    """BASELINE configs[4] (the reference has no mixed-width batching): one G16 bucket with STN/TPS on and
+    one G32 bucket with STN off, each trained for a step in the same process; both must match the oracle."""
+    for case in ("tatt_g16_stn_train_n3", "tatt_g32_train_n2"):
+        net, sd, x, tp, cls, kw, N, training = make(case)
+        out, aux = net(x.to(DEV), tp.to(DEV))
+        o_out, _, _ = run_oracle(cls, kw, sd, x, tp, training)
+        assert relerr(out, o_out) <= 1e-3
+        out.mean().backward()
+        assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
