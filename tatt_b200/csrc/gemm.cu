@@ -732,6 +732,10 @@ int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv2d_wgrad: too many pixels");
   cudaStream_t st = (cudaStream_t)stream;
   TATT_CUDA(cudaMemsetAsync(dWt, 0, sizeof(float) * (size_t)KH * KW * Cin * Cout, st));
+  if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout == 64 && ws && !(flags & F_FP32)) {
+    int rc = tatt_tc3_conv3x3_wgrad_launch(X, dY, dWt, nimg, H, W, ws, ws_bytes, st);
+    if (rc >= 0) return rc;
+  }
   GemmP p = {};
   p.A = X; p.B = dY; p.C = dWt; p.bias = nullptr;
   p.M = KH * KW * Cin; p.N = Cout; p.K = nimg * H * W;

@@ -219,6 +219,138 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dWt[(tap,ci)][co] += sum_px X[px + tap][ci] * dY[px][co]  for the same 3x3 / 64->64 conv.  The reduction axis is the
+// pixel axis, so both operands are MN-major tiles whose rows are pixels (128 B = 64 bf16 channels).  One k-tile =
+// 64 pixels of one image row: ONE TMA halo load (3 rows x 66 px, hi+lo) + one dY tile serve all nine taps -- five
+// 128-row M-tiles (taps 2i, 2i+1 as the two 64-channel MN blocks of a descriptor, LBO = byte distance between the two
+// shifted halo windows), accumulated in five 64-column TMEM accumulators over the CTA's share of the pixels, then
+// added to global memory with atomics (split-K over CTAs).
+constexpr int WG_HALO_ROWS = 3 * 66;
+constexpr int WG_X_PLANE = ((WG_HALO_ROWS * 128 + 1023) / 1024) * 1024;   // 25600
+constexpr int WG_STAGE = 2 * WG_X_PLANE + 2 * 64 * 128;                   // X hi, X lo, dY hi, dY lo
+constexpr int WG_NSTAGE = 3;
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                         const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
+                         float* __restrict__ dWt, int H, int W, int total_tiles, int tiles_per_cta) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long bar_done, bar_full[WG_NSTAGE], bar_empty[WG_NSTAGE];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t0 = blockIdx.x * tiles_per_cta;
+  int t1 = t0 + tiles_per_cta;
+  if (t1 > total_tiles) t1 = total_tiles;
+  const int nt = t1 - t0;
+  const int nxs = W / 64;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_done), 1);
+    for (int s = 0; s < WG_NSTAGE; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % WG_NSTAGE;
+        if (i >= WG_NSTAGE) mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((i / WG_NSTAGE) - 1) & 1));
+        const int t = t0 + i;
+        const int xs = t % nxs, y = (t / nxs) % H, n = t / (nxs * H);
+        const uint32_t st = sbase + (uint32_t)(s * WG_STAGE);
+        const uint32_t bar = smem_u32(&bar_full[s]);
+        mbar_expect_tx(bar, 2u * (uint32_t)(WG_HALO_ROWS * 128) + 2u * 64u * 128u);
+        tma_load_4d(st, &tmXh, bar, 0, xs * 64 - 1, y - 1, n);
+        tma_load_4d(st + WG_X_PLANE, &tmXl, bar, 0, xs * 64 - 1, y - 1, n);
+        tma_load_4d(st + 2 * WG_X_PLANE, &tmGh, bar, 0, xs * 64, y, n);
+        tma_load_4d(st + 2 * WG_X_PLANE + 64 * 128, &tmGl, bar, 0, xs * 64, y, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // M = 128, N = 64, A and B MN-major (bits 15, 16)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % WG_NSTAGE;
+        mbar_wait(smem_u32(&bar_full[s]), (uint32_t)((i / WG_NSTAGE) & 1));
+        tc_fence_after();
+        const uint32_t st = sbase + (uint32_t)(s * WG_STAGE);
+        const uint32_t x_hi = st, x_lo = st + WG_X_PLANE, g_hi = st + 2 * WG_X_PLANE, g_lo = g_hi + 64 * 128;
+#pragma unroll
+        for (int mt = 0; mt < 5; ++mt) {
+          const int ta = 2 * mt, tb = (2 * mt + 1 < 9) ? 2 * mt + 1 : 2 * mt;
+          const uint32_t offa = (uint32_t)(((ta / 3) * 66 + (ta % 3)) * 128);
+          const uint32_t offb = (uint32_t)(((tb / 3) * 66 + (tb % 3)) * 128);
+          const uint32_t lbo = (tb != ta) ? (offb - offa) : 128u;
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint32_t ko = k16 * 2048;   // 16 pixel rows
+            const uint64_t dah = make_desc_mn(x_hi + offa + ko, lbo), dal = make_desc_mn(x_lo + offa + ko, lbo);
+            const uint64_t dbh = make_desc_mn(g_hi + ko, 8192), dbl = make_desc_mn(g_lo + ko, 8192);
+            const uint32_t tm = tmem_base + (uint32_t)(mt * 64);
+            umma_bf16(tm, dal, dbh, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+            umma_bf16(tm, dah, dbl, idesc, 1u);
+            umma_bf16(tm, dah, dbh, idesc, 1u);
+          }
+        }
+        umma_commit(smem_u32(&bar_empty[s]));
+      }
+      umma_commit(smem_u32(&bar_done));
+    }
+  } else if (nt > 0) {
+    mbar_wait(smem_u32(&bar_done), 0);
+    tc_fence_after();
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;              // row of the 128-row M tile: (m >= 64) selects the second tap
+#pragma unroll
+    for (int mt = 0; mt < 5; ++mt) {
+      const int tap = 2 * mt + (m >> 6);
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * 64 + c16 * 16), v);
+        if (tap < 9) {
+          float* dst = dWt + ((long long)(tap * 64 + (m & 63))) * 64 + c16 * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -289,5 +421,47 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
   const int grid = nimg * (H / R) * (W / TW);
   conv3x3_tma_kernel<R><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, mode == 2 ? 1 : 0);
   TATT_LAUNCH_CHECK("conv3x3_tma_kernel");
+  return 0;
+}
+
+// conv3x3 64->64 weight gradient through the TMA kernel; dWt must be zeroed by the caller.  Same return convention.
+int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, void* ws,
+                                  long long ws_bytes, cudaStream_t st) {
+  static const int mode = []() {
+    const char* e = getenv("TATT_TMA_WGRAD");
+    return e ? atoi(e) : 1;
+  }();
+  if (mode == 0 || ws == nullptr || W % 64 != 0) return -1;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  const long long P = (long long)nimg * H * W;
+  const long long nA = rup8(P * 64);
+  if ((long long)sizeof(__nv_bfloat16) * 4 * nA > ws_bytes || (((uintptr_t)ws) & 15)) return -1;
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16 *Xh = base, *Xl = base + nA, *Gh = base + 2 * nA, *Gl = base + 3 * nA;
+  int rc = tatt_tc2_split(X, 64, P, 64, 0, Xh, Xl, nullptr, st);
+  if (rc) return rc;
+  rc = tatt_tc2_split(dY, 64, P, 64, 0, Gh, Gl, nullptr, st);
+  if (rc) return rc;
+  CUtensorMap tm[4];
+  cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+  cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t boxX[4] = {64, 66, 3, 1}, boxG[4] = {64, 64, 1, 1};
+  void* ptrs[4] = {Xh, Xl, Gh, Gl};
+  for (int i = 0; i < 4; ++i) {
+    CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptrs[i], gdim, gstr, i < 2 ? boxX : boxG, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return tatt_set_error("cuTensorMapEncodeTiled(wgrad) failed: %d", (int)r);
+  }
+  const int total = (int)(P / 64);
+  int grid = total < 148 ? total : 148;
+  const int per = (total + grid - 1) / grid;
+  grid = (total + per - 1) / per;
+  const int smem = WG_NSTAGE * WG_STAGE + 1024;
+  TATT_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  conv3x3_wgrad_tma_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tm[3], dWt, H, W, total, per);
+  TATT_LAUNCH_CHECK("conv3x3_wgrad_tma_kernel");
   return 0;
 }
