@@ -243,7 +243,8 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_by
 __global__ void __launch_bounds__(192, 1)
 conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                          const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
-                         float* __restrict__ dWt, int H, int W, int total_tiles, int tiles_per_cta) {
+                         float* __restrict__ dWt, float* __restrict__ partial, int H, int W, int total_tiles,
+                         int tiles_per_cta) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) unsigned long long bar_done, bar_full[WG_NSTAGE], bar_empty[WG_NSTAGE];
@@ -337,9 +338,18 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * 64 + c16 * 16), v);
         if (tap < 9) {
-          float* dst = dWt + ((long long)(tap * 64 + (m & 63))) * 64 + c16 * 16;
+          const long long off = ((long long)(tap * 64 + (m & 63))) * 64 + c16 * 16;
+          if (partial) {       // per-CTA partial tile, summed by wgrad_reduce_kernel (no same-address atomics)
+            float4* dst = reinterpret_cast<float4*>(partial + (long long)blockIdx.x * (576 * 64) + off);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+            for (int q = 0; q < 4; ++q)
+              dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          } else {
+            float* dst = dWt + off;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          }
         }
       }
     }
@@ -349,6 +359,14 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int c = 0; c < nparts; ++c) a += partial[(long long)c * n + i];
+  out[i] = a;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -436,7 +454,8 @@ int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, i
   if (!enc) return -1;
   const long long P = (long long)nimg * H * W;
   const long long nA = rup8(P * 64);
-  if ((long long)sizeof(__nv_bfloat16) * 4 * nA > ws_bytes || (((uintptr_t)ws) & 15)) return -1;
+  const long long plane_bytes = (long long)sizeof(__nv_bfloat16) * 4 * nA;
+  if (plane_bytes > ws_bytes || (((uintptr_t)ws) & 15)) return -1;
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16 *Xh = base, *Xl = base + nA, *Gh = base + 2 * nA, *Gl = base + 3 * nA;
   int rc = tatt_tc2_split(X, 64, P, 64, 0, Xh, Xl, nullptr, st);
@@ -460,8 +479,17 @@ int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, i
   const int per = (total + grid - 1) / grid;
   grid = (total + per - 1) / per;
   const int smem = WG_NSTAGE * WG_STAGE + 1024;
+  // per-CTA partial tiles live behind the planes when the workspace is large enough
+  float* partial = nullptr;
+  const long long part_bytes = (long long)grid * 576 * 64 * sizeof(float);
+  if (ws_bytes >= plane_bytes + part_bytes + 16)
+    partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + ((plane_bytes + 15) & ~15LL));
   TATT_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  conv3x3_wgrad_tma_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tm[3], dWt, H, W, total, per);
+  conv3x3_wgrad_tma_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tm[3], dWt, partial, H, W, total, per);
   TATT_LAUNCH_CHECK("conv3x3_wgrad_tma_kernel");
+  if (partial) {
+    wgrad_reduce_kernel<<<(576 * 64 + 255) / 256, 256, 0, st>>>(partial, dWt, grid, 576 * 64);
+    TATT_LAUNCH_CHECK("wgrad_reduce_kernel");
+  }
   return 0;
 }

@@ -247,7 +247,7 @@ def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True,
             db = colsum(dy.view(-1, cout_p))[:co]
     elif need_dw:
         dwt = empty(kh * kw * cin_p, cout_p, like=x)
-        ws, wsb = _ws(x, x.numel() + n * h * wd * _r8(cout_p))
+        ws, wsb = _ws(x, x.numel() + n * h * wd * _r8(cout_p) + 148 * kh * kw * cin_p * cout_p + 16)
         _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dy), _p(dwt), n, h, wd, cin_p, cout_p, kh, kw, pad, pad, _precision_flag,
                    _p(ws), wsb, _stream())
         dw = empty(co, ci, kh, kw, like=x)
