@@ -30,6 +30,7 @@ enum { K2_DENSE_K = 0, K2_IM2COL_K = 1, K2_DENSE_MN = 2, K2_IM2COL_MN = 3 };
 struct Tc2P {
   const __nv_bfloat16 *Ahi, *Alo, *Bhi, *Blo;
   float* C;
+  float* partial;                 // split-K: per-split partial tiles [splitk][batch][M][N] (NULL -> atomics on C)
   const float* bias;
   int M, N, K;
   long long lda, ldb, ldc;        // plane leading dimensions (elements) / C leading dimension
@@ -337,7 +338,12 @@ __global__ void __launch_bounds__(NT, (STAGES <= 2) ? 2 : 1) tc2_gemm_kernel(con
             if (bias && zs == 0 && gn < p.N) v[j] += __ldg(bias + gn);
           }
           const int gq = gn0 + 4 * q;
-          if (atomic) {
+          if (atomic && p.partial) {
+            float* pd = p.partial + (((long long)zs * p.batch + zb) * p.M + gm) * p.N + gq;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (gq + j < p.N) pd[j] = v[j];
+          } else if (atomic) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (gq + j < p.N) atomicAdd(dst + 4 * q + j, v[j]);
@@ -522,6 +528,21 @@ static int launch_kind(const Tc2P& q, cudaStream_t st) {
 
 }  // namespace
 
+// C[b][m][n] += sum_s partial[s][b][m][n]
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int splitk, int batch,
+                                     int M, int N, long long ldc, long long sC) {
+  const long long per = (long long)batch * M * N;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= per) return;
+  float a = 0.f;
+  for (int s = 0; s < splitk; ++s) a += partial[(long long)s * per + i];
+  const int n = (int)(i % N);
+  const long long r = i / N;
+  const int m = (int)(r % M);
+  const int b = (int)(r / M);
+  C[(long long)b * sC + (long long)m * ldc + n] += a;
+}
+
 // planes [rows][rup8(cols)] (transpose == 0) or [cols][rup8(rows)] (transpose == 1), zero padded
 int tatt_tc2_split(const float* src, long long ld, long long rows, int cols, int transpose, void* hi, void* lo,
                    float* colsum, cudaStream_t st) {
@@ -686,10 +707,28 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
     q.flags |= F_ATOMIC;
     q.flags &= ~(F_RELU | F_ACCUM);
   }
-  switch (kind) {
-    case K2_DENSE_K: return launch_kind<K2_DENSE_K>(q, st);
-    case K2_IM2COL_K: return launch_kind<K2_IM2COL_K>(q, st);
-    case K2_DENSE_MN: return launch_kind<K2_DENSE_MN>(q, st);
-    default: return launch_kind<K2_IM2COL_MN>(q, st);
+  // split-K results: per-split partial tiles in the tail of the workspace + one reduction, instead of splitk-way
+  // same-address atomics (the caller has zeroed / pre-filled C either way)
+  q.partial = nullptr;
+  if (split && q.splitk > 1 && ws != nullptr) {
+    const long long used = (long long)sizeof(__nv_bfloat16) * 2 * (nA8 + nB8);
+    const long long need = (long long)q.splitk * p.batch * p.M * p.N * (long long)sizeof(float);
+    const long long off = (used + 255) & ~255LL;
+    if (p.M * (long long)p.N <= 1 << 20 && off + need <= ws_bytes)
+      q.partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + off);
   }
+  int rc;
+  switch (kind) {
+    case K2_DENSE_K: rc = launch_kind<K2_DENSE_K>(q, st); break;
+    case K2_IM2COL_K: rc = launch_kind<K2_IM2COL_K>(q, st); break;
+    case K2_DENSE_MN: rc = launch_kind<K2_DENSE_MN>(q, st); break;
+    default: rc = launch_kind<K2_IM2COL_MN>(q, st); break;
+  }
+  if (rc == 0 && q.partial) {
+    const long long per = (long long)p.batch * p.M * p.N;
+    splitk_reduce_kernel<<<(int)((per + 255) / 256), 256, 0, st>>>(q.partial, p.C, q.splitk, p.batch, p.M, p.N, p.ldc,
+                                                                   p.sC);
+    TATT_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
+  return rc;
 }

@@ -74,8 +74,12 @@ def gemm(amode: int, bmode: int, A: Tensor, lda: int, B: Tensor, ldb: int, C: Te
          sC: int = 0, sBias: int = 0, loA: int = 0, loB: int = 0) -> None:
     """flags & F_APLANES / F_BPLANES: A / B are bf16 hi planes (see Planes), lo plane at +loA / +loB elements."""
     ws, wsb = (None, 0)
-    if M >= 32 and K >= 32 and N > 4 and not (flags & F_APLANES and flags & F_BPLANES):
-        ws, wsb = _ws(C, batch * (_r8(M) * _r8(K) + _r8(N) * _r8(K)))
+    if M >= 32 and K >= 32 and N > 4:
+        ne = 0 if (flags & F_APLANES and flags & F_BPLANES) else batch * (_r8(M) * _r8(K) + _r8(N) * _r8(K))
+        if flags & F_SPLITK or (M <= 256 and K >= 512):     # room for the split-K partial tiles (<= 148 splits)
+            ne += 150 * batch * M * N + 128
+        if ne:
+            ws, wsb = _ws(C, ne)
     _cabi.call("tatt_gemm", amode, bmode, _p(A), lda, _p(B), ldb, _p(C), ldc, _p(bias), M, N, K, batch, sA, sB,
                sC, sBias, flags | _precision_flag, loA, loB, _p(ws), wsb, _stream())
 
