@@ -243,6 +243,27 @@ def run_ours(args):
     clocks = sampler.stop()
     timed(1, True)
     ms_e2e, _ = timed(args.steps, True)
+
+    # forward-only (inference) throughput of the same model / batch, eval mode, CUDA graph, inputs resident
+    from tatt_b200.train import GraphedForward
+    fwd = GraphedForward(model, (B, 4, h, w), (B, 37, 1, 26))
+    fwd.x.copy_(x_d); fwd.text.copy_(tp_d)
+    fwd.capture()
+    for _ in range(3):
+        fwd()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        fwd()
+    f1.record()
+    barrier()
+    ms_fwd = f0.elapsed_time(f1)
+    if world > 1:
+        tf = torch.tensor([ms_fwd], device=dev)
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        ms_fwd = tf.item()
+    model.train()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -268,6 +289,9 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (x_h.numel() + tp_h.numel()) * 4, "d2h_bytes_per_step": 4},
+            "forward_only": {"value": B * world * args.steps / (ms_fwd * 1e-3), "unit": UNIT,
+                             "ms_per_step": ms_fwd / args.steps,
+                             "note": "eval-mode forward of the same batch, CUDA graph, cached positional encoding"},
             "roofline": roof}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(kw, h, w, args.cpu_sample, 2, 1)

@@ -710,7 +710,12 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
   // split-K results: per-split partial tiles in the tail of the workspace + one reduction, instead of splitk-way
   // same-address atomics (the caller has zeroed / pre-filled C either way)
   q.partial = nullptr;
-  if (split && q.splitk > 1 && ws != nullptr) {
+  // measured: not a win for the generic engine at these sizes (36.7 vs 36.0 ms/step) -> opt-in only
+  static const bool partial_on = []() {
+    const char* e = getenv("TATT_SPLITK_PARTIAL");
+    return e && e[0] == '1';
+  }();
+  if (partial_on && want_split && q.splitk > 1 && ws != nullptr) {
     const long long used = (long long)sizeof(__nv_bfloat16) * 2 * (nA8 + nB8);
     const long long need = (long long)q.splitk * p.batch * p.M * p.N * (long long)sizeof(float);
     const long long off = (used + 255) & ~255LL;

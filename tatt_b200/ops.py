@@ -76,8 +76,6 @@ def gemm(amode: int, bmode: int, A: Tensor, lda: int, B: Tensor, ldb: int, C: Te
     ws, wsb = (None, 0)
     if M >= 32 and K >= 32 and N > 4:
         ne = 0 if (flags & F_APLANES and flags & F_BPLANES) else batch * (_r8(M) * _r8(K) + _r8(N) * _r8(K))
-        if flags & F_SPLITK or (M <= 256 and K >= 512):     # room for the split-K partial tiles (<= 148 splits)
-            ne += 150 * batch * M * N + 128
         if ne:
             ws, wsb = _ws(C, ne)
     _cabi.call("tatt_gemm", amode, bmode, _p(A), lda, _p(B), ldb, _p(C), ldc, _p(bias), M, N, K, batch, sA, sB,

@@ -167,3 +167,43 @@ class GraphedTrainer(Trainer):
         self._allreduce()
         self.graph_opt.replay()
         return self.out
+
+
+class GraphedForward:
+    """Eval-mode forward (`model(x, text_emb)` under no_grad) captured into one CUDA graph for fixed shapes.  The
+    recurrent positional encoding depends on the weights only, so it is computed once (cached by the module)."""
+
+    def __init__(self, model: torch.nn.Module, x_shape, text_shape):
+        self.model = model.eval()
+        dev = next(model.parameters()).device
+        self.x = torch.zeros(x_shape, dtype=torch.float32, device=dev)
+        self.text = torch.zeros(text_shape, dtype=torch.float32, device=dev) if text_shape is not None else None
+        self.graph = None
+        self.out = None
+
+    def _run(self):
+        with torch.no_grad():
+            res = self.model(self.x, self.text) if self.text is not None else self.model(self.x)
+        return res
+
+    def capture(self, warmup: int = 2) -> None:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+
+    def __call__(self, x: Optional[Tensor] = None, text_emb: Optional[Tensor] = None):
+        if self.graph is None:
+            self.capture()
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if text_emb is not None:
+            self.text.copy_(text_emb, non_blocking=True)
+        self.graph.replay()
+        return self.out
