@@ -103,7 +103,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 template <int KIND, int STAGES>
-__global__ void __launch_bounds__(NT, (STAGES <= 2) ? 2 : 1) tc2_gemm_kernel(const Tc2P p) {
+__global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1)) tc2_gemm_kernel(const Tc2P p) {
   constexpr bool MN = (KIND == K2_DENSE_MN || KIND == K2_IM2COL_MN);
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -257,52 +257,90 @@ __global__ void __launch_bounds__(NT, (STAGES <= 2) ? 2 : 1) tc2_gemm_kernel(con
   // ------------------------------------------------------------------ main loop
   uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   if (MN) idesc |= (1u << 15) | (1u << 16);
+  if (STAGES == 1) {
+    // single-stage variant for K <= 64 (one k-tile): 49 KB of shared memory -> 4 CTAs per SM hide the latency
+    for (int kt = 0; kt < nk; ++kt) {
+      if (kt >= 1) mbar_wait(smem_u32(&mma_done[0]), (uint32_t)((kt - 1) & 1));
+      issue_loads(kt);
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t st = smem_base;
+        const uint32_t a_hi = st, a_lo = st + A_PLANE, b_hi = st + 2 * A_PLANE, b_lo = b_hi + B_PLANE;
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nk) issue_loads(s);
-    cp_async_commit();
-  }
-  for (int kt = 0; kt < nk; ++kt) {
-    const int s = kt % STAGES;
-    cp_async_wait<STAGES - 2>();
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t st = smem_base + (uint32_t)(s * STAGE_BYTES);
-      const uint32_t a_hi = st, a_lo = st + A_PLANE, b_hi = st + 2 * A_PLANE, b_lo = b_hi + B_PLANE;
-#pragma unroll
-      for (int k16 = 0; k16 < BK / 16; ++k16) {
-        uint64_t dah, dal, dbh, dbl;
-        if (!MN) {
-          const uint32_t ko = k16 * 32;      // 16 bf16 along K inside the 128-byte swizzle atom
-          dah = make_desc(a_hi + ko, 16, 1024);
-          dal = make_desc(a_lo + ko, 16, 1024);
-          dbh = make_desc(b_hi + ko, 16, 1024);
-          dbl = make_desc(b_lo + ko, 16, 1024);
-        } else {
-          const uint32_t ko = k16 * 2048;    // 16 k-rows = two 8-row groups of 1024 B
-          dah = make_desc(a_hi + ko, 8192, 1024);
-          dal = make_desc(a_lo + ko, 8192, 1024);
-          dbh = make_desc(b_hi + ko, 8192, 1024);
-          dbl = make_desc(b_lo + ko, 8192, 1024);
+        for (int k16 = 0; k16 < BK / 16; ++k16) {
+          uint64_t dah, dal, dbh, dbl;
+          if (!MN) {
+            const uint32_t ko = k16 * 32;
+            dah = make_desc(a_hi + ko, 16, 1024);
+            dal = make_desc(a_lo + ko, 16, 1024);
+            dbh = make_desc(b_hi + ko, 16, 1024);
+            dbl = make_desc(b_lo + ko, 16, 1024);
+          } else {
+            const uint32_t ko = k16 * 2048;
+            dah = make_desc(a_hi + ko, 8192, 1024);
+            dal = make_desc(a_lo + ko, 8192, 1024);
+            dbh = make_desc(b_hi + ko, 8192, 1024);
+            dbl = make_desc(b_lo + ko, 8192, 1024);
+          }
+          umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_base, dah, dbh, idesc, 1u);
         }
-        umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
-        umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-        umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        umma_commit(smem_u32(&mma_done[0]));
       }
-      umma_commit(smem_u32(&mma_done[s]));
     }
-    // refill the stage consumed at iteration kt-1 (its MMAs were committed to mma_done[(kt-1)%STAGES])
-    const int nxt = kt + STAGES - 1;
-    if (nxt < nk) {
-      if (kt >= 1) {
-        const int ps = (kt - 1) % STAGES;
-        mbar_wait(smem_u32(&mma_done[ps]), (uint32_t)(((kt - 1) / STAGES) & 1));
+  } else {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nk) issue_loads(s);
+      cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % STAGES;
+      cp_async_wait<STAGES - 2>();
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t st = smem_base + (uint32_t)(s * STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + A_PLANE, b_hi = st + 2 * A_PLANE, b_lo = b_hi + B_PLANE;
+  #pragma unroll
+        for (int k16 = 0; k16 < BK / 16; ++k16) {
+          uint64_t dah, dal, dbh, dbl;
+          if (!MN) {
+            const uint32_t ko = k16 * 32;      // 16 bf16 along K inside the 128-byte swizzle atom
+            dah = make_desc(a_hi + ko, 16, 1024);
+            dal = make_desc(a_lo + ko, 16, 1024);
+            dbh = make_desc(b_hi + ko, 16, 1024);
+            dbl = make_desc(b_lo + ko, 16, 1024);
+          } else {
+            const uint32_t ko = k16 * 2048;    // 16 k-rows = two 8-row groups of 1024 B
+            dah = make_desc(a_hi + ko, 8192, 1024);
+            dal = make_desc(a_lo + ko, 8192, 1024);
+            dbh = make_desc(b_hi + ko, 8192, 1024);
+            dbl = make_desc(b_lo + ko, 8192, 1024);
+          }
+          umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(smem_u32(&mma_done[s]));
       }
-      issue_loads(nxt);
+      // refill the stage consumed at iteration kt-1 (its MMAs were committed to mma_done[(kt-1)%STAGES])
+      const int nxt = kt + STAGES - 1;
+      if (nxt < nk) {
+        if (kt >= 1) {
+          const int ps = (kt - 1) % STAGES;
+          mbar_wait(smem_u32(&mma_done[ps]), (uint32_t)(((kt - 1) / STAGES) & 1));
+        }
+        issue_loads(nxt);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
   }
 
   // ------------------------------------------------------------------ epilogue
@@ -522,6 +560,7 @@ static int launch_kind(const Tc2P& q, cudaStream_t st) {
   }();
   constexpr bool kMN = (KIND == K2_DENSE_MN || KIND == K2_IM2COL_MN);
   const bool long_k = (KIND == K2_DENSE_K) && (q.kper / BK >= 12);      // e.g. the RPE recurrent GEMMs
+  if (KIND == K2_DENSE_K && q.kper <= BK) return launch_kind_s<KIND, 1>(q, st);   // one k-tile: 4 CTAs/SM
   if (((kMN || long_k) ? stages_mn : stages) == 4) return launch_kind_s<KIND, 4>(q, st);
   return launch_kind_s<KIND, 2>(q, st);
 }
