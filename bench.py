@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python (no CUDA graphs)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="f32 (default, the configuration BASELINE.json's metric is quoted on: fp32 parity via "
+                         "bf16 hi/lo split MMAs) or bf16 (configs 3/4: single-plane bf16 operands, fp32 accumulate)")
     return ap.parse_args()
 
 
@@ -147,7 +150,7 @@ def conv_roofline(dev, batch, h, w, peaks):
         y = torch.empty_like(x)
         e0.record()
         _cabi.call("tatt_conv2d_igemm", x.data_ptr(), wtp.data_ptr(), b.data_ptr(), y.data_ptr(), batch, h, w, 64, 64,
-                   3, 3, 1, 1, 0, ws.data_ptr(), wsb, ops._stream())
+                   3, 3, 1, 1, ops._precision_flag, ws.data_ptr(), wsb, ops._stream())
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e-3)
@@ -162,7 +165,8 @@ def conv_roofline(dev, batch, h, w, peaks):
             "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak,
             "traffic": traffic, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if "bf16_tflops" in peaks
             else "fallback 1.59 PFLOP/s, of fallback", "launch_ms": t * 1e3, "algorithmic_flops_per_launch": flops,
-            "note": "fp32-parity mode costs 3 bf16 MMAs per product, so the ceiling of this kernel is 1/3 of the bf16 peak"}
+            "note": "fp32-parity mode costs 3 bf16 MMAs per product, so the ceiling of this kernel is 1/3 of the bf16 peak"
+            if not (ops._precision_flag & ops.F_BF16) else "bf16 mode: one MMA per product"}
 
 
 def run_ours(args):
@@ -185,6 +189,7 @@ def run_ours(args):
     torch.manual_seed(1234)
     model = tatt_b200.TSRN_TL_TRANS(**kw).to(dev).train()
     tatt_b200.manual_seed(1234 + rank)
+    tatt_b200.set_precision("bf16" if args.dtype == "bf16" else "fp32")
     B = args.batch
     if args.eager:
         trainer = Trainer(model)
@@ -280,7 +285,7 @@ def run_ours(args):
     roof["model_algorithmic_tflops"] = value * ALG_FLOPS_FWD_BWD_G32 / 1e12 if args.geometry == "g32" else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "TSRN_TL_TRANS(width=%d,height=%d,STN=%s) fwd+bwd+clip+Adam, per-GPU batch %d, "
                                    "train mode dropout 0.1" % (kw["width"], kw["height"], kw["STN"], B),
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,

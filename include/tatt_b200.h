@@ -28,7 +28,8 @@ int tatt_arch(void);
  * model/tsrn.py:170,1070 ; model/transformer_v2.py:453-458,785-790,177 ; model/stn_head.py:49-53
  * amode: 0 A[M][K] row-major, 1 A given as [K][M].  bmode: 0 B[K][N], 1 B given as [N][K].
  * flags: 1 accumulate into C, 2 ReLU epilogue, 4 split-K with atomics (C must be zero, or add 64 to
- * have a dense C zeroed here), 128 force the fp32 FFMA kernels instead of the tcgen05 bf16x3 path.
+ * have a dense C zeroed here), 128 force the fp32 FFMA kernels instead of the tcgen05 bf16x3 path, 1024 bf16 mode
+ * (operands rounded to bf16, one MMA per k-step, fp32 accumulate; also honoured by the conv entry points).
  * ws / ws_bytes: optional device scratch (16-byte aligned, >= 4*(|A|+|B|) bytes rounded up per row to 8
  * elements) for the pre-split bf16 operand planes of the v2 tcgen05 engine; NULL selects the in-loop split.  batch > 1 strides A/B/C/bias by sA/sB/sC/sBias elements. */
 int tatt_gemm(int amode, int bmode, const float* A, long long lda, const float* B, long long ldb, float* C,

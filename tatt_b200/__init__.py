@@ -13,3 +13,9 @@ def manual_seed(seed: int) -> None:
     """Seed the device-resident dropout RNG streams (graph-capture safe Philox state)."""
     from .ops import DeviceRNG
     DeviceRNG.manual_seed(seed)
+
+
+def set_precision(mode: str) -> None:
+    """'fp32' (default, bf16 hi/lo split x3 MMAs = fp32-grade parity), 'bf16' (single-plane bf16 MMAs), 'ffma'."""
+    from . import ops
+    ops.set_precision(mode)

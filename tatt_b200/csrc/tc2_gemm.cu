@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
   const int umma_n = (nvalid + 15) & ~15;
   const int nk = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
   const uint32_t smem_base = smem_u32(smem);
+  const bool single = (p.flags & F_BF16) != 0;   // bf16 mode: hi plane only, one MMA per k-step
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&mma_done[s]), 1);
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
         if (!ok) off = 0;
         const uint32_t d = (uint32_t)(row * 128 + ((ch ^ (row & 7)) << 4));
         cp_async16(a_hi + d, Ahi + off, ok ? 16 : 0);
-        cp_async16(a_lo + d, Alo + off, ok ? 16 : 0);
+        if (!single) cp_async16(a_lo + d, Alo + off, ok ? 16 : 0);
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
         const long long off = ok ? (long long)gn * p.ldb + gk : 0;
         const uint32_t d = (uint32_t)(row * 128 + ((ch ^ (row & 7)) << 4));
         cp_async16(b_hi + d, Bhi + off, ok ? 16 : 0);
-        cp_async16(b_lo + d, Blo + off, ok ? 16 : 0);
+        if (!single) cp_async16(b_lo + d, Blo + off, ok ? 16 : 0);
       }
     } else {
 #pragma unroll
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
         if (!ok) off = 0;
         const uint32_t d = (uint32_t)(mm * 8192 + k * 128 + ((ch ^ (k & 7)) << 4));
         cp_async16(a_hi + d, Ahi + off, ok ? 16 : 0);
-        cp_async16(a_lo + d, Alo + off, ok ? 16 : 0);
+        if (!single) cp_async16(a_lo + d, Alo + off, ok ? 16 : 0);
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
         const long long off = ok ? (long long)gk * p.ldb + gn : 0;
         const uint32_t d = (uint32_t)(k * 128 + ((ch ^ (k & 7)) << 4));
         cp_async16(b_hi + d, Bhi + off, ok ? 16 : 0);
-        cp_async16(b_lo + d, Blo + off, ok ? 16 : 0);
+        if (!single) cp_async16(b_lo + d, Blo + off, ok ? 16 : 0);
       }
     }
   };
@@ -286,9 +287,13 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
             dbh = make_desc(b_hi + ko, 8192, 1024);
             dbl = make_desc(b_lo + ko, 8192, 1024);
           }
-          umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+          if (!single) {
+            umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+          } else {
+            umma_bf16(tmem_base, dah, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+          }
         }
         umma_commit(smem_u32(&mma_done[0]));
       }
@@ -324,9 +329,13 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
             dbh = make_desc(b_hi + ko, 8192, 1024);
             dbl = make_desc(b_lo + ko, 8192, 1024);
           }
-          umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+          if (!single) {
+            umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+          } else {
+            umma_bf16(tmem_base, dah, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+          }
         }
         umma_commit(smem_u32(&mma_done[s]));
       }
@@ -706,7 +715,7 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
   q.M = p.M; q.N = p.N; q.K = p.K;
   q.ldc = p.ldc; q.sC = p.sC; q.sBias = p.sBias;
   q.batch = p.batch;
-  q.flags = p.flags & (F_ACCUM | F_RELU | F_VECC);
+  q.flags = p.flags & (F_ACCUM | F_RELU | F_VECC | F_BF16);
   q.cH = p.cH; q.cW = p.cW; q.cC = p.cC; q.KH = p.KH; q.KW = p.KW; q.padH = p.padH; q.padW = p.padW;
   q.fdHW = p.fdHW; q.fdW = p.fdW; q.fdC = p.fdC; q.fdKW = p.fdKW;
   q.fdCB = make_fd(p.cC >= 64 ? p.cC / 64 : 1);

@@ -97,7 +97,8 @@ template <int R>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                   float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int base_off_mode) {
+                   float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int base_off_mode,
+                   int single) {
   constexpr int A_ROWS = (R + 2) * HALO_W;
   constexpr int A_PLANE = ((A_ROWS * 128 + 1023) / 1024) * 1024;
   constexpr int TMEM_COLS = (R * 64 <= 64) ? 64 : ((R * 64 <= 128) ? 128 : 256);
@@ -138,16 +139,16 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(smem_u32(&bar_a), 2u * (uint32_t)(A_ROWS * 128));
+      mbar_expect_tx(smem_u32(&bar_a), (single ? 1u : 2u) * (uint32_t)(A_ROWS * 128));
       tma_load_4d(a_hi, &tmAh, smem_u32(&bar_a), 0, x0 - 1, y0 - 1, n);
-      tma_load_4d(a_lo, &tmAl, smem_u32(&bar_a), 0, x0 - 1, y0 - 1, n);
+      if (!single) tma_load_4d(a_lo, &tmAl, smem_u32(&bar_a), 0, x0 - 1, y0 - 1, n);
       for (int tap = 0; tap < 9; ++tap) {
         const int s = tap % NSTAGE;
         if (tap >= NSTAGE) mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((tap / NSTAGE) - 1) & 1));
         const uint32_t dst = b_ring + (uint32_t)(s * B_TAP_BYTES);
-        mbar_expect_tx(smem_u32(&bar_full[s]), (uint32_t)B_TAP_BYTES);
+        mbar_expect_tx(smem_u32(&bar_full[s]), (uint32_t)(single ? B_TAP_BYTES / 2 : B_TAP_BYTES));
         tma_load_2d(dst, &tmBh, smem_u32(&bar_full[s]), tap * 64, 0);
-        tma_load_2d(dst + 64 * 128, &tmBl, smem_u32(&bar_full[s]), tap * 64, 0);
+        if (!single) tma_load_2d(dst + 64 * 128, &tmBl, smem_u32(&bar_full[s]), tap * 64, 0);
       }
     }
   } else if (warp == 1) {
@@ -173,9 +174,13 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             const uint64_t dah = make_desc(sa_h, bo_h), dal = make_desc(sa_l, bo_l);
             const uint64_t dbh = make_desc(b_hi + ko, 0), dbl = make_desc(b_lo + ko, 0);
             const uint32_t tm = tmem_base + (uint32_t)(r * 64);
-            umma_bf16(tm, dal, dbh, idesc, (tap > 0 || k16 > 0) ? 1u : 0u);
-            umma_bf16(tm, dah, dbl, idesc, 1u);
-            umma_bf16(tm, dah, dbh, idesc, 1u);
+            if (!single) {
+              umma_bf16(tm, dal, dbh, idesc, (tap > 0 || k16 > 0) ? 1u : 0u);
+              umma_bf16(tm, dah, dbl, idesc, 1u);
+              umma_bf16(tm, dah, dbh, idesc, 1u);
+            } else {
+              umma_bf16(tm, dah, dbh, idesc, (tap > 0 || k16 > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(smem_u32(&bar_empty[s]));
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(192, 1)
 conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                          const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
                          float* __restrict__ dWt, float* __restrict__ partial, int H, int W, int total_tiles,
-                         int tiles_per_cta) {
+                         int tiles_per_cta, int single) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) unsigned long long bar_done, bar_full[WG_NSTAGE], bar_empty[WG_NSTAGE];
@@ -286,11 +291,11 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
         const int xs = t % nxs, y = (t / nxs) % H, n = t / (nxs * H);
         const uint32_t st = sbase + (uint32_t)(s * WG_STAGE);
         const uint32_t bar = smem_u32(&bar_full[s]);
-        mbar_expect_tx(bar, 2u * (uint32_t)(WG_HALO_ROWS * 128) + 2u * 64u * 128u);
+        mbar_expect_tx(bar, (single ? 1u : 2u) * ((uint32_t)(WG_HALO_ROWS * 128) + 64u * 128u));
         tma_load_4d(st, &tmXh, bar, 0, xs * 64 - 1, y - 1, n);
-        tma_load_4d(st + WG_X_PLANE, &tmXl, bar, 0, xs * 64 - 1, y - 1, n);
+        if (!single) tma_load_4d(st + WG_X_PLANE, &tmXl, bar, 0, xs * 64 - 1, y - 1, n);
         tma_load_4d(st + 2 * WG_X_PLANE, &tmGh, bar, 0, xs * 64, y, n);
-        tma_load_4d(st + 2 * WG_X_PLANE + 64 * 128, &tmGl, bar, 0, xs * 64, y, n);
+        if (!single) tma_load_4d(st + 2 * WG_X_PLANE + 64 * 128, &tmGl, bar, 0, xs * 64, y, n);
       }
     }
   } else if (warp == 1) {
@@ -316,9 +321,13 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
             const uint64_t dah = make_desc_mn(x_hi + offa + ko, lbo), dal = make_desc_mn(x_lo + offa + ko, lbo);
             const uint64_t dbh = make_desc_mn(g_hi + ko, 8192), dbl = make_desc_mn(g_lo + ko, 8192);
             const uint32_t tm = tmem_base + (uint32_t)(mt * 64);
-            umma_bf16(tm, dal, dbh, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
-            umma_bf16(tm, dah, dbl, idesc, 1u);
-            umma_bf16(tm, dah, dbh, idesc, 1u);
+            if (!single) {
+              umma_bf16(tm, dal, dbh, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+              umma_bf16(tm, dah, dbl, idesc, 1u);
+              umma_bf16(tm, dah, dbh, idesc, 1u);
+            } else {
+              umma_bf16(tm, dah, dbh, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(smem_u32(&bar_empty[s]));
@@ -389,7 +398,7 @@ static inline long long rup8(long long x) { return (x + 7) & ~7LL; }
 
 // conv3x3 64->64 through the TMA kernel.  Returns 0 ok, 1 error, -1 not eligible (caller falls through).
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
-                            void* ws, long long ws_bytes, cudaStream_t st) {
+                            int single, void* ws, long long ws_bytes, cudaStream_t st) {
   static const int mode = []() {          // TATT_TMA: 0 = off, 1 = on (base_offset 0), 2 = on (base_offset from address)
     const char* e = getenv("TATT_TMA");
     return e ? atoi(e) : 1;
@@ -437,14 +446,14 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
   const int smem = 2 * A_PLANE + NSTAGE * B_TAP_BYTES + 1024;
   TATT_CUDA(cudaFuncSetAttribute(conv3x3_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = nimg * (H / R) * (W / TW);
-  conv3x3_tma_kernel<R><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, mode == 2 ? 1 : 0);
+  conv3x3_tma_kernel<R><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, mode == 2 ? 1 : 0, single);
   TATT_LAUNCH_CHECK("conv3x3_tma_kernel");
   return 0;
 }
 
 // conv3x3 64->64 weight gradient through the TMA kernel; dWt must be zeroed by the caller.  Same return convention.
-int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, void* ws,
-                                  long long ws_bytes, cudaStream_t st) {
+int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int single,
+                                  void* ws, long long ws_bytes, cudaStream_t st) {
   static const int mode = []() {
     const char* e = getenv("TATT_TMA_WGRAD");
     return e ? atoi(e) : 1;
@@ -485,7 +494,7 @@ int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, i
   if (ws_bytes >= plane_bytes + part_bytes + 16)
     partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + ((plane_bytes + 15) & ~15LL));
   TATT_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  conv3x3_wgrad_tma_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tm[3], dWt, partial, H, W, total, per);
+  conv3x3_wgrad_tma_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tm[3], dWt, partial, H, W, total, per, single);
   TATT_LAUNCH_CHECK("conv3x3_wgrad_tma_kernel");
   if (partial) {
     wgrad_reduce_kernel<<<(576 * 64 + 255) / 256, 256, 0, st>>>(partial, dWt, grid, 576 * 64);

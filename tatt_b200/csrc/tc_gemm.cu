@@ -376,9 +376,13 @@ __global__ void __launch_bounds__(NT, (BN == 64) ? 2 : 1) tc_gemm_kernel(const G
         const uint32_t ko = k16 * 32;   // 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom
         const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
         const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-        umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);   // small terms first
-        umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-        umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        if (!(p.flags & F_BF16)) {
+          umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);   // small terms first
+          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        } else {
+          umma_bf16(tmem_base, dah, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);   // bf16 mode
+        }
       }
       umma_commit(smem_u32(&mma_done[s]));
     }

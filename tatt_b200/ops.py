@@ -11,8 +11,20 @@ from . import _cabi
 
 Tensor = torch.Tensor
 ACT_NONE, ACT_RELU, ACT_MISH = 0, 1, 2
-F_ACCUM, F_RELU, F_SPLITK, F_ZEROC, F_FP32, F_APLANES, F_BPLANES = 1, 2, 4, 64, 128, 256, 512
+F_ACCUM, F_RELU, F_SPLITK, F_ZEROC, F_FP32, F_APLANES, F_BPLANES, F_BF16 = 1, 2, 4, 64, 128, 256, 512, 1024
 _precision_flag = 0      # OR-ed into every GEMM / conv call; F_FP32 inside `full_fp32()`
+
+
+def set_precision(mode: str) -> None:
+    """'fp32' (default): fp32 parity on tensor cores via the bf16 hi/lo split (3 MMAs per k-step);
+    'bf16': operands rounded to bf16, one MMA per k-step, fp32 accumulation (BASELINE configs 3/4);
+    'ffma': every GEMM / convolution on the fp32 CUDA-core kernels."""
+    global _precision_flag
+    _precision_flag = {"fp32": 0, "bf16": F_BF16, "ffma": F_FP32}[mode]
+
+
+def get_precision() -> str:
+    return "ffma" if _precision_flag & F_FP32 else ("bf16" if _precision_flag & F_BF16 else "fp32")
 
 
 class full_fp32:
