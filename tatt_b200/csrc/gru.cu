@@ -7,6 +7,7 @@
 //      over the BATCH axis): per-step gate kernels around the batched recurrent GEMM (gemm.cu).
 // Gate order r,z,n; n = tanh(gi_n + r * (W_hn h + b_hn)); h' = (1-z) n + z h   (torch.nn.GRU).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -357,6 +358,22 @@ __global__ void rpe_gate_bwd_kernel(const float* __restrict__ dQPOS, const float
 
 }  // namespace
 
+// warp-level tensor-core scans (gru_mma.cu); TATT_GRU_MMA=0 selects the scalar kernels above
+int tatt_gru32_scan_fwd_mma_launch(const float* GI, const float* Whh, const float* bhh, float* OUT, float* GATES,
+                                   int nseq, int T, int s_inner, long long outer_stride, long long inner_stride,
+                                   long long t_stride, cudaStream_t st);
+int tatt_gru32_scan_bwd_mma_launch(const float* dOUT, const float* GATES, const float* Whh, float* dGI, float* dGH,
+                                   int nseq, int T, int s_inner, long long outer_stride, long long inner_stride,
+                                   long long t_stride, cudaStream_t st);
+static bool gru_mma_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TATT_GRU_MMA");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 extern "C" {
 
 // rows are addressed as base(seq) + t*t_stride, base(seq) = (seq / s_inner)*outer_stride + (seq % s_inner)*inner_stride
@@ -365,6 +382,9 @@ int tatt_gru32_scan_fwd(const float* GI, const float* Whh, const float* bhh, flo
                         void* stream) {
   if (nseq <= 0 || T <= 0) return 0;
   TATT_REQUIRE(s_inner >= 1, "gru32_scan_fwd: s_inner must be >= 1");
+  if (gru_mma_enabled())
+    return tatt_gru32_scan_fwd_mma_launch(GI, Whh, bhh, OUT, GATES, nseq, T, s_inner, outer_stride, inner_stride,
+                                          t_stride, (cudaStream_t)stream);
   long long warps = 2LL * ((nseq + 1) / 2);
   int blocks = (int)((warps + 3) / 4);
   gru32_scan_fwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(GI, Whh, bhh, OUT, GATES, nseq, T, s_inner,
@@ -378,6 +398,9 @@ int tatt_gru32_scan_bwd(const float* dOUT, const float* GATES, const float* Whh,
                         void* stream) {
   if (nseq <= 0 || T <= 0) return 0;
   TATT_REQUIRE(s_inner >= 1, "gru32_scan_bwd: s_inner must be >= 1");
+  if (gru_mma_enabled())
+    return tatt_gru32_scan_bwd_mma_launch(dOUT, GATES, Whh, dGI, dGH, nseq, T, s_inner, outer_stride, inner_stride,
+                                          t_stride, (cudaStream_t)stream);
   long long warps = 2LL * ((nseq + 1) / 2);
   int blocks = (int)((warps + 3) / 4);
   gru32_scan_bwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(dOUT, GATES, Whh, dGI, dGH, nseq, T, s_inner,

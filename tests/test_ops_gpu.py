@@ -131,7 +131,10 @@ def test_layernorm():
 
 
 # ------------------------------------------------------------------------------------------ GRU(32)
-@pytest.mark.parametrize("N,H,W,vertical", [(2, 16, 64, True), (2, 16, 64, False), (3, 5, 7, True), (3, 5, 7, False)])
+# the last two shapes have enough sequences (>= 16 * 4 * 148 / 2) for the 16-rows-per-warp variant of the MMA scan,
+# one of them ragged (nseq % 16 != 0); the small ones run the 8-rows-per-warp variant
+@pytest.mark.parametrize("N,H,W,vertical", [(2, 16, 64, True), (2, 16, 64, False), (3, 5, 7, True), (3, 5, 7, False),
+                                            (40, 4, 128, True), (37, 3, 131, True)])
 def test_bigru32_scan(N, H, W, vertical):
     from tatt_b200 import ops
     from tatt_b200.tape import Tape
