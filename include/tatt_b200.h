@@ -46,6 +46,30 @@ int tatt_split_bf16(const float* src, long long ld, long long rows, int cols, in
 /* out[c] (+)= sum_r X[r*ldx + c] */
 int tatt_colsum(const float* X, long long ldx, float* out, long long P, int C, int zero_first, void* stream);
 
+/* ---- per-pixel linear layers with the operand split fused into the loader (tc4_rows.cu) ----------
+ * GruBlock.conv1 (1x1 conv over the channel concatenation, model/tsrn.py:902,1075), nn.GRU weight_ih
+ * (tsrn.py:1071), attention in/out projections and FFN of the TP Interpreter
+ * (model/transformer_v2.py:453-458,785-790): Y[M][N] (=|+=) act(sum_kb X_kb[M][64] W[:, 64kb:64kb+64]^T + bias)
+ * over M pixel / token rows, fp32 in HBM, read once.  KB = 1..3 K blocks of 64 columns, each from its own
+ * tensor (row strides ldx*; the concatenation never exists in memory); N in {64,128,192}, KB*N <= 192.
+ * wtrans = 0: W[N][64 KB] (row stride ldw); 1: W given as [64 KB][N] (data gradient: Y = dY W).
+ * flags: 1 accumulate into Y, 2 ReLU, 1024 bf16 mode (see tatt_gemm). */
+int tatt_rows_gemm(const float* X0, long long ldx0, const float* X1, long long ldx1, const float* X2, long long ldx2,
+                   const float* W, long long ldw, int wtrans, const float* bias, float* Y, long long ldy, long long M,
+                   int N, int KB, int flags, void* stream);
+/* Weight gradients of the same layers: D[64][64 NB] = A[M][64]^T B[M][64 NB], reduction over the M rows.
+ * A's 64 columns are two 32-column segments a_off0 / a_off1 of its rows (a_off1 = a_off0 + 32 for a plain
+ * matrix; the saved h_{t-1} of both GRU directions are two separate segments of the gate tensor);
+ * B0..B2 are NB column blocks of 64.  out[b][i][j] = D[b rb + (T ? j : i)][b cb + (T ? i : j)] for b < nb,
+ * i < ni, j < nj (T = transpose): e.g. dW[N][K] of a linear layer with A = dY, B = X (T = 0), or
+ * dW_ih[192][64] with A = X, B = dGI (T = 1).  colsum_src 1 / 2: dbias[n] = column sums of A / of B (the bias
+ * gradient), n < nbias.  ws: scratch of tatt_rows_wgrad_ws_bytes() bytes for per-CTA partial tiles. */
+int tatt_rows_wgrad_ws_bytes(void);
+int tatt_rows_wgrad(const float* A, long long lda, int a_off0, int a_off1, const float* B0, long long ldb0,
+                    const float* B1, long long ldb1, const float* B2, long long ldb2, int NB, long long M,
+                    int colsum_src, float* out, int nb, int ni, int nj, int transpose, int rb, int cb, float* dbias,
+                    int nbias, void* ws, long long ws_bytes, int flags, void* stream);
+
 /* ---- convolution (stride 1), implicit GEMM over NHWC: nn.Conv2d ------------------------------------
  * model/tsrn.py:597 (9x9 stem), 876,884 (SRB 3x3), 611 (block7), 1043 (upsample 64->256), 623 (9x9 out);
  * model/stn_head.py:15.  Weights are first packed to Wt[(ky,kx,ci)][co] (flip=0) or, for the

@@ -82,7 +82,7 @@ def last_error() -> str:
 _KERNELS = {"tatt_bn_stats": 2, "tatt_bn_bwd": 3, "tatt_memcpy_d2d": 0, "tatt_memset0": 0,
             # GEMM / conv entry points split their fp32 operands into bf16 planes first (2 passes unless the caller
             # passes pre-split planes); counted as the common case
-            "tatt_gemm": 3, "tatt_conv2d_igemm": 3, "tatt_conv2d_wgrad": 3}
+            "tatt_gemm": 3, "tatt_conv2d_igemm": 3, "tatt_conv2d_wgrad": 3, "tatt_rows_wgrad": 2}
 launch_count = 0
 
 

@@ -1,0 +1,609 @@
+// Row-panel GEMMs of the per-pixel linear layers with the fp32 -> bf16 hi/lo operand split FUSED into the loader.
+//
+// Every 1x1 convolution / nn.Linear / GRU input projection of the path (model/tsrn.py:1070,1075 GruBlock.conv1,
+// nn.GRU weight_ih; model/transformer_v2.py:453-458,785-790 attention in/out projections and FFN) is a GEMM
+// Y[P][N] = X[P][K] W[N][K]^T over P = N*H*W pixel rows with K, N in {64, 128, 192}: ~1 FLOP per byte, i.e. bound
+// by HBM, not by the tensor cores.  The v2 engine (tc2_gemm.cu) needs its operands pre-split into bf16 planes, which
+// costs one extra read + write of every activation map (split_dense / split_colsum passes: ~20 % of a training step,
+// profiles/r1b_launches_by_kernel.txt).  Here the fp32 rows are read ONCE, split in registers on their way into the
+// canonical SWIZZLE_128B shared-memory tiles, and consumed by tcgen05.mma (3 MMAs per k-step: lo*hi + hi*lo + hi*hi,
+// fp32 accumulate in TMEM -- the same fp32-parity scheme as the rest of the engine):
+//
+//   rows_gemm_kernel   forward / data-gradient:  Y (=|+=) act(sum_kb X_kb[P][64] W[:, 64kb:64kb+64]^T + b)
+//                      persistent over 128-row tiles, the (pre-split) weights stay resident in shared memory, the
+//                      next tile is prefetched into registers while the current one is in the tensor pipe / epilogue,
+//                      the epilogue goes TMEM -> registers -> swizzled staging -> 128-byte coalesced row stores.
+//                      Up to three 64-column K blocks may come from different tensors (the channel concatenation of
+//                      tsrn.py:902 never exists in memory).
+//   rows_wgrad_kernel  weight gradient:  D[64][64*NB] = A[P][64]^T B[P][64*NB] (reduction over the pixel rows, both
+//                      operands MN-major: a shared-memory row is one pixel's 64 channels), column sums of A or B (the
+//                      bias gradient) accumulated in the loader registers, per-CTA partial tiles + a reduction kernel
+//                      (deterministic, no same-address atomics).
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "gemm_params.cuh"
+
+namespace {
+
+constexpr int RB = 128;            // pixel rows per tile / slab
+constexpr int NT = 256;
+constexpr int PLANE = RB * 128;    // bytes of one bf16 plane of a [128 rows][64 ch] slab
+constexpr int WG_LD = 192;         // row stride of a per-CTA partial tile
+constexpr int WG_PART = 64 * WG_LD + WG_LD;   // floats: D[64][192] + colsum[192]
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// SWIZZLE_128B shared-memory descriptor (cute::UMMA::SmemDescriptor): version 1 at [46,48), layout type 2 at [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// 8 consecutive fp32 -> 8 bf16 hi (16 B) + 8 bf16 lo (16 B); element 0 at the lowest address
+__device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    const float2 hf = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// One [128 rows][64 cols] fp32 slab in flight per CTA: thread `tid` owns the 16-byte bf16 chunk ch = tid & 7 of rows
+// (tid >> 3) + 32 i, i = 0..3 (two float4 loads each; a warp covers 4 rows x 256 B -- fully coalesced).
+struct Slab {
+  float4 v[8];
+};
+// columns of chunk ch: ch < 4 -> o0 + 8 ch, else o1 + 8 (ch - 4)  (two 32-column segments; o1 = o0 + 32 when contiguous)
+__device__ __forceinline__ void slab_load(Slab& s, const float* __restrict__ src, long long ld, int o0, int o1,
+                                          long long row0, long long M, int tid) {
+  const int ch = tid & 7;
+  const int col = (ch < 4) ? (o0 + ch * 8) : (o1 + (ch - 4) * 8);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long gm = row0 + (tid >> 3) + 32 * i;
+    if (gm < M) {
+      const float4* q = reinterpret_cast<const float4*>(src + gm * ld + col);
+      s.v[2 * i] = __ldg(q);
+      s.v[2 * i + 1] = __ldg(q + 1);
+    } else {
+      s.v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s.v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+// split + store into a SWIZZLE_128B tile whose rows are the slab rows (128 B = 64 bf16 per row)
+__device__ __forceinline__ void slab_store(const Slab& s, unsigned char* hi, unsigned char* lo, bool single, int tid) {
+  const int ch = tid & 7;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = (tid >> 3) + 32 * i;
+    uint4 h, l;
+    split8(s.v[2 * i], s.v[2 * i + 1], h, l);
+    const int off = row * 128 + ((ch ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    if (!single) *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward / dgrad
+struct RowsP {
+  const float *X0, *X1, *X2;   // K blocks (64 columns each)
+  long long ldx0, ldx1, ldx2;
+  const float* W;              // W[N][K] (wtrans = 0) or W[K][N] (wtrans = 1), row stride ldw
+  long long ldw;
+  int wtrans;
+  const float* bias;
+  float* Y;
+  long long ldy;
+  long long M;
+  int N, KB, flags, ntiles;
+};
+
+__global__ void __launch_bounds__(NT, 2) rows_gemm_kernel(const RowsP p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool single = (p.flags & F_BF16) != 0;
+  const int N = p.N, KB = p.KB;
+  const int wtile = N * 128;               // bytes of one K block of one W plane ([N rows][128 B])
+  unsigned char* w_hi = smem;
+  unsigned char* w_lo = smem + KB * wtile;
+  unsigned char* a_hi = smem + 2 * KB * wtile;
+  unsigned char* a_lo = a_hi + PLANE;
+  const uint32_t tmem_cols = (N <= 64) ? 64u : ((N <= 128) ? 128u : 256u);
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // weights: split once, resident for the whole kernel (K-major tiles, row n = output channel n)
+  for (int idx = tid; idx < KB * N * 8; idx += NT) {
+    const int ch = idx & 7;
+    const int rn = idx >> 3;
+    const int kb = rn / N, n = rn - kb * N;
+    float4 a, b;
+    if (!p.wtrans) {
+      const float4* q = reinterpret_cast<const float4*>(p.W + (long long)n * p.ldw + kb * 64 + ch * 8);
+      a = __ldg(q);
+      b = __ldg(q + 1);
+    } else {
+      const float* q = p.W + (long long)(kb * 64 + ch * 8) * p.ldw + n;
+      a = make_float4(__ldg(q), __ldg(q + p.ldw), __ldg(q + 2 * p.ldw), __ldg(q + 3 * p.ldw));
+      b = make_float4(__ldg(q + 4 * p.ldw), __ldg(q + 5 * p.ldw), __ldg(q + 6 * p.ldw), __ldg(q + 7 * p.ldw));
+    }
+    uint4 h, l;
+    split8(a, b, h, l);
+    const int off = kb * wtile + n * 128 + ((ch ^ (n & 7)) << 4);
+    *reinterpret_cast<uint4*>(w_hi + off) = h;
+    if (!single) *reinterpret_cast<uint4*>(w_lo + off) = l;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bar_a = smem_u32(&bar);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(RB >> 4) << 24);
+  const bool accum = (p.flags & F_ACCUM) != 0, relu = (p.flags & F_RELU) != 0;
+  const int lg = warp & 3, half = warp >> 2;
+
+  Slab pre;
+  int tile = blockIdx.x, kb = 0;
+  uint32_t ph = 0;
+  bool pending = false;
+  if (tile < p.ntiles) slab_load(pre, p.X0, p.ldx0, 0, 32, (long long)tile * RB, p.M, tid);
+  while (tile < p.ntiles) {
+    if (pending) {               // MMAs of the previous K block still read the stage
+      mbar_wait(bar_a, ph);
+      ph ^= 1;
+      pending = false;
+    }
+    slab_store(pre, a_hi, a_lo, single, tid);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
+      const uint32_t bh = smem_u32(w_hi) + (uint32_t)(kb * wtile), bl = smem_u32(w_lo) + (uint32_t)(kb * wtile);
+#pragma unroll
+      for (int k16 = 0; k16 < 4; ++k16) {
+        const uint32_t ko = k16 * 32;   // 16 bf16 along K inside the 128-byte swizzle atom
+        const uint64_t dah = make_desc(ah + ko, 16, 1024), dal = make_desc(al + ko, 16, 1024);
+        const uint64_t dbh = make_desc(bh + ko, 16, 1024), dbl = make_desc(bl + ko, 16, 1024);
+        const uint32_t acc = (kb > 0 || k16 > 0) ? 1u : 0u;
+        if (!single) {
+          umma_bf16(tmem_base, dal, dbh, idesc, acc);
+          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        } else {
+          umma_bf16(tmem_base, dah, dbh, idesc, acc);
+        }
+      }
+      umma_commit(bar_a);
+    }
+    pending = true;
+    // prefetch the next (tile, K block) into registers: in flight during the MMAs and the epilogue
+    int ntile = tile, nkb = kb + 1;
+    if (nkb == KB) {
+      nkb = 0;
+      ntile = tile + gridDim.x;
+    }
+    if (ntile < p.ntiles) {
+      const float* xs = (nkb == 0) ? p.X0 : ((nkb == 1) ? p.X1 : p.X2);
+      const long long ls = (nkb == 0) ? p.ldx0 : ((nkb == 1) ? p.ldx1 : p.ldx2);
+      slab_load(pre, xs, ls, 0, 32, (long long)ntile * RB, p.M, tid);
+    }
+    if (kb == KB - 1) {
+      mbar_wait(bar_a, ph);
+      ph ^= 1;
+      pending = false;
+      tc_fence_after();
+      // epilogue: the stage (32 KB = [128 rows][2 halves][128 B]) doubles as a warp-private transposition buffer
+      const int row = lg * 32 + lane;
+      unsigned char* stg = a_hi;
+      for (int j = 0; j * 64 < N; ++j) {
+        const int col0 = j * 64 + half * 32;
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(col0 + 16 * c16), v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = 4 * c16 + q;
+            float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                   __uint_as_float(v[4 * q + 3]));
+            if (p.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * c));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(stg + row * 256 + half * 128 + ((c ^ (row & 7)) << 4)) = o;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = lg * 32 + 4 * i + (lane >> 3), c = lane & 7;
+          float4 o = *reinterpret_cast<const float4*>(stg + r * 256 + half * 128 + ((c ^ (r & 7)) << 4));
+          const long long gm = (long long)tile * RB + r;
+          if (gm < p.M) {
+            float4* dst = reinterpret_cast<float4*>(p.Y + gm * p.ldy + col0 + 4 * c);
+            if (accum) {
+              const float4 old = *dst;
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            if (relu) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            *dst = o;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncthreads();          // stage + accumulator free for the next tile
+    }
+    tile = ntile;
+    kb = nkb;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+struct WgP {
+  const float* A;              // [M][lda]; columns a_off0..+32 and a_off1..+32 form the 64 "A channels"
+  long long lda;
+  int a_off0, a_off1;
+  const float *B0, *B1, *B2;   // NB slabs of 64 columns
+  long long ldb0, ldb1, ldb2;
+  int NB;
+  long long M;
+  int nblk;
+  float* partial;              // [gridDim.x][WG_PART]
+  int colsum_src;              // 0 none, 1 A (64 sums), 2 B (64 NB sums)
+  int flags;
+};
+
+__global__ void __launch_bounds__(NT, 2) rows_wgrad_kernel(const WgP p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[WG_LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool single = (p.flags & F_BF16) != 0;
+  // A: two 64-channel MN blocks per plane (the MMA's M is 128; block 1 is zero padding), B: one block per plane
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = smem + 2 * PLANE;
+  unsigned char* b_hi = smem + 4 * PLANE;
+  unsigned char* b_lo = smem + 5 * PLANE;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < PLANE / 16; i += NT) {
+    *reinterpret_cast<uint4*>(a_hi + PLANE + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(a_lo + PLANE + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int i = tid; i < WG_LD; i += NT) red[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bar_a = smem_u32(&bar);
+  // M = 128, N = 64, A and B MN-major (bits 15, 16)
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
+  const int NB = p.NB;
+  float cs[3][8];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cs[j][q] = 0.f;
+
+  Slab pre;
+  uint32_t ph = 0;
+  bool pending = false;
+  int blk = blockIdx.x;
+  bool first = true;
+  if (blk < p.nblk) slab_load(pre, p.A, p.lda, p.a_off0, p.a_off1, (long long)blk * RB, p.M, tid);
+  while (blk < p.nblk) {
+    const int nblk_next = blk + gridDim.x;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      if (s <= NB) {
+        if (pending) {           // the previous MMA group still reads A / B
+          mbar_wait(bar_a, ph);
+          ph ^= 1;
+          pending = false;
+        }
+        if (s == 0) {
+          slab_store(pre, a_hi, a_lo, single, tid);
+          if (p.colsum_src == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              cs[0][0] += pre.v[2 * i].x; cs[0][1] += pre.v[2 * i].y; cs[0][2] += pre.v[2 * i].z; cs[0][3] += pre.v[2 * i].w;
+              cs[0][4] += pre.v[2 * i + 1].x; cs[0][5] += pre.v[2 * i + 1].y; cs[0][6] += pre.v[2 * i + 1].z;
+              cs[0][7] += pre.v[2 * i + 1].w;
+            }
+          }
+        } else {
+          slab_store(pre, b_hi, b_lo, single, tid);
+          if (p.colsum_src == 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float* c = cs[(s > 0) ? (s - 1) : 0];
+              c[0] += pre.v[2 * i].x; c[1] += pre.v[2 * i].y; c[2] += pre.v[2 * i].z; c[3] += pre.v[2 * i].w;
+              c[4] += pre.v[2 * i + 1].x; c[5] += pre.v[2 * i + 1].y; c[6] += pre.v[2 * i + 1].z;
+              c[7] += pre.v[2 * i + 1].w;
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        // prefetch the next slab: B_s of this block, or A of the CTA's next block
+        if (s < NB) {
+          const float* bs = (s == 0) ? p.B0 : ((s == 1) ? p.B1 : p.B2);
+          const long long ls = (s == 0) ? p.ldb0 : ((s == 1) ? p.ldb1 : p.ldb2);
+          slab_load(pre, bs, ls, 0, 32, (long long)blk * RB, p.M, tid);
+        } else if (nblk_next < p.nblk) {
+          slab_load(pre, p.A, p.lda, p.a_off0, p.a_off1, (long long)nblk_next * RB, p.M, tid);
+        }
+        if (s >= 1) {
+          if (tid == 0) {
+            tc_fence_after();
+            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+            const uint32_t tm = tmem_base + (uint32_t)((s - 1) * 64);
+#pragma unroll
+            for (int k16 = 0; k16 < 8; ++k16) {
+              const uint32_t ko = k16 * 2048;   // 16 pixel rows = two 8-row groups of 1024 B
+              const uint64_t dah = make_desc(ah + ko, PLANE, 1024), dal = make_desc(al + ko, PLANE, 1024);
+              const uint64_t dbh = make_desc(bh + ko, PLANE, 1024), dbl = make_desc(bl + ko, PLANE, 1024);
+              const uint32_t acc = (!first || k16 > 0) ? 1u : 0u;
+              if (!single) {
+                umma_bf16(tm, dal, dbh, idesc, acc);
+                umma_bf16(tm, dah, dbl, idesc, 1u);
+                umma_bf16(tm, dah, dbh, idesc, 1u);
+              } else {
+                umma_bf16(tm, dah, dbh, idesc, acc);
+              }
+            }
+            umma_commit(bar_a);
+          }
+          pending = true;
+        }
+      }
+    }
+    first = false;
+    blk = nblk_next;
+  }
+  if (pending) {
+    mbar_wait(bar_a, ph);
+    ph ^= 1;
+  }
+  tc_fence_after();
+  float* part = p.partial + (long long)blockIdx.x * WG_PART;
+  const int lg = warp & 3, half = warp >> 2;
+  const bool any = blockIdx.x < p.nblk;
+  if (lg < 2) {                      // D rows 64..127 belong to the zero half of A
+    const int row = lg * 32 + lane;
+    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+      for (int c16 = 0; c16 < 2; ++c16) {
+        uint32_t v[16];
+        const int col0 = j * 64 + half * 32 + c16 * 16;
+        if (any) {
+          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)col0, v);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0u;
+        }
+        float4* dst = reinterpret_cast<float4*>(part + row * WG_LD + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                               __uint_as_float(v[4 * q + 3]));
+      }
+    }
+  }
+  if (p.colsum_src) {
+    const int ch = tid & 7;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int o = ch * 8 + q;
+        if (j < ((p.colsum_src == 1) ? 1 : NB)) atomicAdd(&red[j * 64 + o], cs[j][q]);
+      }
+    __syncthreads();
+    for (int i = tid; i < WG_LD; i += NT) part[64 * WG_LD + i] = red[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// out[b][i][j] = sum_parts D[b rb + (T ? j : i)][b cb + (T ? i : j)];  dbias[n] = sum_parts colsum[n]
+__global__ void rows_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ out, int nb,
+                                         int ni, int nj, int T, int rb, int cb, float* __restrict__ dbias, int nbias) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = nb * ni * nj;
+  long long src;
+  float* dst;
+  if (idx < total) {
+    const int b = idx / (ni * nj), rem = idx - b * ni * nj;
+    const int i = rem / nj, j = rem - i * nj;
+    const int r = b * rb + (T ? j : i), c = b * cb + (T ? i : j);
+    src = (long long)r * WG_LD + c;
+    dst = out + idx;
+  } else if (idx - total < nbias) {
+    src = 64LL * WG_LD + (idx - total);
+    dst = dbias + (idx - total);
+  } else {
+    return;
+  }
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int c = 0;
+  for (; c + 3 < nparts; c += 4) {
+    a0 += partial[(long long)c * WG_PART + src];
+    a1 += partial[(long long)(c + 1) * WG_PART + src];
+    a2 += partial[(long long)(c + 2) * WG_PART + src];
+    a3 += partial[(long long)(c + 3) * WG_PART + src];
+  }
+  for (; c < nparts; ++c) a0 += partial[(long long)c * WG_PART + src];
+  *dst = (a0 + a1) + (a2 + a3);
+}
+
+static int num_sms() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
+}
+static bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int tatt_rows_gemm(const float* X0, long long ldx0, const float* X1, long long ldx1, const float* X2, long long ldx2,
+                   const float* W, long long ldw, int wtrans, const float* bias, float* Y, long long ldy, long long M,
+                   int N, int KB, int flags, void* stream) {
+  TATT_REQUIRE(M >= 1 && (N == 64 || N == 128 || N == 192) && KB >= 1 && KB <= 3 && KB * N <= 192,
+               "tatt_rows_gemm: unsupported shape M=%lld N=%d K=%d", M, N, 64 * KB);
+  TATT_REQUIRE(X0 && W && Y && (KB < 2 || X1) && (KB < 3 || X2), "tatt_rows_gemm: null operand");
+  TATT_REQUIRE(al16(X0) && al16(X1) && al16(X2) && al16(Y) && al16(bias) && (wtrans || al16(W)) && ldx0 % 4 == 0 &&
+                   ldx1 % 4 == 0 && ldx2 % 4 == 0 && ldy % 4 == 0 && (wtrans || ldw % 4 == 0),
+               "tatt_rows_gemm: operands must be 16-byte aligned with row strides that are multiples of 4");
+  RowsP p;
+  p.X0 = X0; p.X1 = X1; p.X2 = X2;
+  p.ldx0 = ldx0; p.ldx1 = ldx1; p.ldx2 = ldx2;
+  p.W = W; p.ldw = ldw; p.wtrans = wtrans;
+  p.bias = bias; p.Y = Y; p.ldy = ldy;
+  p.M = M; p.N = N; p.KB = KB; p.flags = flags;
+  p.ntiles = (int)((M + RB - 1) / RB);
+  const int smem = 2 * KB * N * 128 + 2 * PLANE + 1024;
+  int grid = 2 * num_sms();
+  if (grid > p.ntiles) grid = p.ntiles;
+  TATT_CUDA(cudaFuncSetAttribute(rows_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  rows_gemm_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(p);
+  TATT_LAUNCH_CHECK("rows_gemm_kernel");
+  return 0;
+}
+
+int tatt_rows_wgrad_ws_bytes(void) { return 2 * 148 * WG_PART * (int)sizeof(float) + 256; }
+
+int tatt_rows_wgrad(const float* A, long long lda, int a_off0, int a_off1, const float* B0, long long ldb0,
+                    const float* B1, long long ldb1, const float* B2, long long ldb2, int NB, long long M,
+                    int colsum_src, float* out, int nb, int ni, int nj, int transpose, int rb, int cb, float* dbias,
+                    int nbias, void* ws, long long ws_bytes, int flags, void* stream) {
+  TATT_REQUIRE(M >= 1 && NB >= 1 && NB <= 3, "tatt_rows_wgrad: unsupported shape M=%lld NB=%d", M, NB);
+  TATT_REQUIRE(A && B0 && (NB < 2 || B1) && (NB < 3 || B2) && out && ws, "tatt_rows_wgrad: null operand");
+  TATT_REQUIRE(al16(A) && al16(B0) && al16(B1) && al16(B2) && al16(ws) && lda % 4 == 0 && ldb0 % 4 == 0 &&
+                   ldb1 % 4 == 0 && ldb2 % 4 == 0 && a_off0 % 4 == 0 && a_off1 % 4 == 0,
+               "tatt_rows_wgrad: operands must be 16-byte aligned with strides / offsets that are multiples of 4");
+  TATT_REQUIRE(colsum_src >= 0 && colsum_src <= 2 && (colsum_src == 0 || dbias) && nbias >= 0 && nbias <= WG_LD,
+               "tatt_rows_wgrad: bad column-sum request");
+  {
+    const int rmax = (nb - 1) * rb + (transpose ? nj : ni), cmax = (nb - 1) * cb + (transpose ? ni : nj);
+    TATT_REQUIRE(nb >= 1 && ni >= 1 && nj >= 1 && rmax <= 64 && cmax <= 64 * NB,
+                 "tatt_rows_wgrad: output map [%d][%d][%d] exceeds the [64][%d] product", nb, ni, nj, 64 * NB);
+  }
+  WgP p;
+  p.A = A; p.lda = lda; p.a_off0 = a_off0; p.a_off1 = a_off1;
+  p.B0 = B0; p.B1 = B1; p.B2 = B2;
+  p.ldb0 = ldb0; p.ldb1 = ldb1; p.ldb2 = ldb2;
+  p.NB = NB; p.M = M;
+  p.nblk = (int)((M + RB - 1) / RB);
+  p.colsum_src = colsum_src; p.flags = flags;
+  int grid = 2 * num_sms();
+  if (grid > 2 * 148) grid = 2 * 148;
+  if (grid > p.nblk) grid = p.nblk;
+  TATT_REQUIRE((long long)grid * WG_PART * (long long)sizeof(float) <= ws_bytes,
+               "tatt_rows_wgrad: workspace too small (%lld bytes, need %lld)", ws_bytes,
+               (long long)grid * WG_PART * (long long)sizeof(float));
+  p.partial = reinterpret_cast<float*>(ws);
+  const int smem = 6 * PLANE + 1024;
+  TATT_CUDA(cudaFuncSetAttribute(rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  rows_wgrad_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(p);
+  TATT_LAUNCH_CHECK("rows_wgrad_kernel");
+  const int total = nb * ni * nj + (colsum_src ? nbias : 0);
+  rows_wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      p.partial, grid, out, nb, ni, nj, transpose, rb, cb, dbias, colsum_src ? nbias : 0);
+  TATT_LAUNCH_CHECK("rows_wgrad_reduce_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -3,7 +3,8 @@ hand-written CUDA kernels of tatt_b200/csrc).  All tensors are fp32 CUDA tensors
 channels-last [N,H,W,C]; "rows" tensors are [P, C] with unit inner stride."""
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import os
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -137,6 +138,101 @@ def split_matrix(x2: Tensor, colsum_out: Optional[Tensor] = None) -> Optional[Ma
     return MatPlanes(t[0], rows * cols, cols)
 
 
+# ---- row-panel kernels with the operand split fused into the loader (csrc/tc4_rows.cu); TATT_ROWS=0 disables them
+_rows_enabled = os.environ.get("TATT_ROWS", "1") != "0"
+
+
+def set_rows_kernels(on: bool) -> None:
+    global _rows_enabled
+    _rows_enabled = bool(on)
+
+
+def _al16(*ts) -> bool:
+    return all(t is None or t.data_ptr() % 16 == 0 for t in ts)
+
+
+def rows_gemm_ok(M: int, K: int, N: int) -> bool:
+    """Y[M,N] = X[M,K] W^T is served by tatt_rows_gemm"""
+    return (_rows_enabled and not (_precision_flag & F_FP32) and M >= 128 and K in (64, 128, 192)
+            and N in (64, 128, 192) and (K // 64) * N <= 192)
+
+
+def rows_wgrad_ok(M: int, N: int, K: int) -> bool:
+    """dW[N,K] = dY[M,N]^T X[M,K] is served by tatt_rows_wgrad"""
+    return (_rows_enabled and not (_precision_flag & F_FP32) and M >= 128
+            and ((N == 64 and K in (64, 128, 192)) or (K == 64 and N in (128, 192))))
+
+
+def _blocks64(x: Tensor) -> List[Tensor]:
+    return [x[:, 64 * i:64 * (i + 1)] for i in range(x.shape[1] // 64)]
+
+
+def rows_gemm(xs: Sequence[Tensor], w: Tensor, b: Optional[Tensor], out: Tensor, wtrans: bool = False,
+              accumulate: bool = False, relu: bool = False) -> Tensor:
+    """out[M,N] (=|+=) act(sum_i xs[i][M,64] @ Wblock_i^T + b); W is [N, 64*len(xs)], or its transpose (wtrans)."""
+    M, KB = xs[0].shape[0], len(xs)
+    N = out.shape[1]
+    args = []
+    for i in range(3):
+        if i < KB:
+            r, c, ld = _rows(xs[i])
+            assert r == M and c == 64, (xs[i].shape,)
+            args += [_p(xs[i]), ld]
+        else:
+            args += [None, 0]
+    wr, wc, ldw = _rows(w)
+    assert (wr, wc) == ((64 * KB, N) if wtrans else (N, 64 * KB)), (w.shape, N, KB, wtrans)
+    _, _, ldo = _rows(out)
+    fl = (F_ACCUM if accumulate else 0) | (F_RELU if relu else 0) | (_precision_flag & F_BF16)
+    _cabi.call("tatt_rows_gemm", *args, _p(w), ldw, 1 if wtrans else 0, _p(b), _p(out), ldo, M, N, KB, fl, _stream())
+    return out
+
+
+def rows_wgrad(A: Tensor, a_offs: Tuple[int, int], Bs: Sequence[Tensor], out: Tensor, nb: int, ni: int, nj: int,
+               transpose: bool, rb: int = 0, cb: int = 0, colsum_src: int = 0, dbias: Optional[Tensor] = None) -> None:
+    """D[64, 64*len(Bs)] = A[:, cols]^T [B0|B1|B2]; out[b,i,j] = D[b*rb + (j if T else i), b*cb + (i if T else j)];
+    dbias = column sums of A (colsum_src 1) or of the B blocks (2)."""
+    M = A.shape[0]
+    lda = A.stride(0)
+    args = []
+    for i in range(3):
+        if i < len(Bs):
+            r, c, ld = _rows(Bs[i])
+            assert r == M and c == 64
+            args += [_p(Bs[i]), ld]
+        else:
+            args += [None, 0]
+    nbytes = _cabi.lib().tatt_rows_wgrad_ws_bytes()
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    assert out.is_contiguous() and out.numel() == nb * ni * nj
+    _cabi.call("tatt_rows_wgrad", _p(A), lda, a_offs[0], a_offs[1], *args, len(Bs), M, colsum_src, _p(out), nb, ni,
+               nj, 1 if transpose else 0, rb, cb, _p(dbias), 0 if dbias is None else dbias.numel(), _p(ws), nbytes,
+               _precision_flag & F_BF16, _stream())
+
+
+def linear_bwd_weight_rows(dy: Tensor, x: Tensor, want_bias: bool, out: Optional[Tensor] = None):
+    """-> (dW[N,K] = dy^T x, db[N] | None) in one pass over dy and x (no pre-split planes)"""
+    M, N, _ = _rows(dy)
+    _, K, _ = _rows(x)
+    if out is None:
+        out = empty(N, K, like=dy)
+    db = empty(N, like=dy) if want_bias else None
+    if N == 64:
+        rows_wgrad(dy, (0, 32), _blocks64(x), out, 1, 64, K, False, colsum_src=1 if want_bias else 0, dbias=db)
+    else:
+        assert K == 64
+        rows_wgrad(x, (0, 32), _blocks64(dy), out, 1, N, 64, True, colsum_src=2 if want_bias else 0, dbias=db)
+    return out, db
+
+
+def linear_bwd_weight_rows_parts(dy: Tensor, parts: Sequence[Tensor], want_bias: bool):
+    """dW[64, 64*len(parts)] = dy^T [part_0 | part_1 | ...] without materialising the concatenation"""
+    out = empty(64, 64 * len(parts), like=dy)
+    db = empty(64, like=dy) if want_bias else None
+    rows_wgrad(dy, (0, 32), list(parts), out, 1, 64, 64 * len(parts), False, colsum_src=1 if want_bias else 0, dbias=db)
+    return out, db
+
+
 def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], out: Optional[Tensor] = None, accumulate: bool = False,
                relu: bool = False, xP: Optional[MatPlanes] = None) -> Tensor:
     """out[M,N] (=|+=) x[M,K] @ w[N,K]^T + b"""
@@ -146,6 +242,8 @@ def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], out: Optional[Tensor] 
     if out is None:
         out = empty(M, N, like=x)
     _, _, ldo = _rows(out)
+    if xP is None and rows_gemm_ok(M, K, N) and ldx % 4 == 0 and ldw % 4 == 0 and ldo % 4 == 0 and _al16(x, w, b, out):
+        return rows_gemm(_blocks64(x), w, b, out, accumulate=accumulate, relu=relu)
     fl = (F_ACCUM if accumulate else 0) | (F_RELU if relu else 0)
     if xP is not None and N > 4:
         gemm(0, 1, xP.hi, xP.ld, w, ldw, out, ldo, b, M, N, K, fl | F_APLANES, loA=xP.lo_off)
@@ -164,6 +262,8 @@ def linear_bwd_data(dy: Tensor, w: Tensor, out: Optional[Tensor] = None, accumul
         out = empty(M, K, like=dy)
     _, _, ldo = _rows(out)
     fl = F_ACCUM if accumulate else 0
+    if dyP is None and rows_gemm_ok(M, N, K) and lddy % 4 == 0 and ldo % 4 == 0 and _al16(dy, w, out):
+        return rows_gemm(_blocks64(dy), w, None, out, wtrans=True, accumulate=accumulate)
     if dyP is not None and K > 4:
         gemm(0, 0, dyP.hi, dyP.ld, w, ldw, out, ldo, None, M, K, N, fl | F_APLANES, loA=dyP.lo_off)
     else:

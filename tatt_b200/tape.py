@@ -62,7 +62,10 @@ class Tape:
 
     def linear(self, x: Tensor, W: Tensor, b: Optional[Tensor], relu: bool = False) -> Tensor:
         """x [M,K] @ W[N,K]^T + b (optionally ReLU)"""
-        xP = ops.split_matrix(x) if self.record else None
+        M, K = x.shape
+        N = W.shape[0]
+        rows = ops.rows_gemm_ok(M, K, N) and ops.rows_gemm_ok(M, N, K) and ops.rows_wgrad_ok(M, N, K)
+        xP = ops.split_matrix(x) if (self.record and not rows) else None
         y = ops.linear_fwd(x, W, b, relu=relu, xP=xP)
 
         def bwd():
@@ -71,6 +74,13 @@ class Tape:
                 return
             if relu:
                 dy = ops.relu_bwd(y, dy)
+            if rows:        # fused-split kernels: one pass over (dy, x) for dW + db, one over dy for dx
+                dW, db = ops.linear_bwd_weight_rows(dy, x, b is not None)
+                self.add_grad(W, dW)
+                if b is not None:
+                    self.add_grad(b, db)
+                self.add_grad(x, ops.linear_bwd_data(dy, W))
+                return
             dyP = self._split_grad(dy, b)
             self.add_grad(W, ops.linear_bwd_weight(dy, x, dyP=dyP, xP=xP))
             self.add_grad(x, ops.linear_bwd_data(dy, W, dyP=dyP))
@@ -81,6 +91,23 @@ class Tape:
         """1x1 convolution over the channel-concatenation of `parts` ([P,Ci] each) without
         materialising the cat (tsrn.py:902 + 1075): y = sum_i parts_i @ W[:, off_i:off_i+Ci]^T + b."""
         W = W4.view(W4.shape[0], -1)
+        M = parts[0].shape[0]
+        rows = (len(parts) <= 3 and all(t.shape[1] == 64 for t in parts) and W.shape[0] == 64
+                and ops.rows_gemm_ok(M, 64 * len(parts), 64) and ops.rows_wgrad_ok(M, 64, 64 * len(parts)))
+        if rows:
+            y = ops.rows_gemm(parts, W, b, ops.empty(M, 64, like=parts[0]))
+
+            def bwd_rows():
+                dy = self.grad(y)
+                if dy is None:
+                    return
+                dW, db = ops.linear_bwd_weight_rows_parts(dy, parts, True)
+                self.add_grad(W4, dW.view_as(W4))
+                self.add_grad(b, db)
+                for i, t in enumerate(parts):
+                    self.add_grad(t, ops.linear_bwd_data(dy, W[:, 64 * i:64 * (i + 1)]))
+            self._push(bwd_rows)
+            return y
         y = None
         off = 0
         pls = []
@@ -295,7 +322,8 @@ class Tape:
             ops.memcpy(bih[d * 96:(d + 1) * 96], b_ih[d])
             ops.memcpy(whh[d], w_hh[d])
             ops.memcpy(bhh[d], b_hh[d])
-        cP = ops.split_matrix(c) if self.record else None
+        rows = ops.rows_gemm_ok(P, 64, 192) and ops.rows_gemm_ok(P, 192, 64) and ops.rows_wgrad_ok(P, 192, 64)
+        cP = ops.split_matrix(c) if (self.record and not rows) else None
         gi = ops.linear_fwd(c, wih, bih, xP=cP)
         out, gates = ops.gru32_scan_fwd(gi, whh, bhh, nseq, T, s_inner, outer, inner, tstride, save=self.record)
         del gi
@@ -305,6 +333,20 @@ class Tape:
             if dout is None:
                 return
             dgi, dgh = ops.gru32_scan_bwd(dout, gates, whh, nseq, T, s_inner, outer, inner, tstride)
+            if rows:
+                dwih, dbih = ops.linear_bwd_weight_rows(dgi, c, True)          # [192, 64], [192]
+                dwhh, dbhh = ops.empty(2, 96, 32, like=c), ops.empty(192, like=c)
+                # dW_hh[d] = dgh[:, 96d:96d+96]^T h_{t-1}[d]: the saved h_{t-1} of both directions (two 32-column
+                # segments of the gate tensor) form the 64 A channels; the diagonal blocks of the product are kept
+                ops.rows_wgrad(gates, (128, 288), ops._blocks64(dgh), dwhh, 2, 96, 32, True, rb=32, cb=96,
+                               colsum_src=2, dbias=dbhh)
+                for d in range(2):
+                    self.add_grad(w_hh[d], dwhh[d])
+                    self.add_grad(b_hh[d], dbhh[d * 96:(d + 1) * 96])
+                    self.add_grad(w_ih[d], dwih[d * 96:(d + 1) * 96])
+                    self.add_grad(b_ih[d], dbih[d * 96:(d + 1) * 96])
+                self.add_grad(c, ops.linear_bwd_data(dgi, wih))
+                return
             dbih, dbhh = ops.empty(192, like=c), ops.empty(192, like=c)
             dgiP, dghP = ops.split_matrix(dgi, dbih), ops.split_matrix(dgh, dbhh)
             if dgiP is None:
@@ -331,7 +373,8 @@ class Tape:
         Wo, bo = attn.out_proj.weight, attn.out_proj.bias
         srcs = (q_in, k_in, v_in)
         sP = [None, None, None]
-        if self.record:
+        rows = all(ops.rows_gemm_ok(t.shape[0], 64, 64) and ops.rows_wgrad_ok(t.shape[0], 64, 64) for t in srcs)
+        if self.record and not rows:
             for i in range(3):
                 for j in range(i):
                     if srcs[i] is srcs[j]:
@@ -352,6 +395,21 @@ class Tape:
         def bwd():
             dy = self.grad(y)
             if dy is None:
+                return
+            if rows:
+                dWo, dbo = ops.linear_bwd_weight_rows(dy, a, True)
+                self.add_grad(Wo, dWo)
+                self.add_grad(bo, dbo)
+                da = ops.linear_bwd_data(dy, Wo)
+                dq, dk, dv = ops.mha_bwd(q, k, v, da, N, Lq, Lk, pdrop, rng_, site)
+                dWin = ops.empty(192, 64, like=dy)
+                dbin = ops.empty(192, like=dy)
+                for i, (g, src) in enumerate(((dq, q_in), (dk, k_in), (dv, v_in))):
+                    _, db_i = ops.linear_bwd_weight_rows(g, src, True, out=dWin[i * 64:(i + 1) * 64])
+                    ops.memcpy(dbin[i * 64:(i + 1) * 64], db_i)
+                    self.add_grad(src, ops.linear_bwd_data(g, Win[i * 64:(i + 1) * 64]))
+                self.add_grad(Win, dWin)
+                self.add_grad(bin_, dbin)
                 return
             dyP = self._split_grad(dy, bo)
             self.add_grad(Wo, ops.linear_bwd_weight(dy, a, dyP=dyP))
