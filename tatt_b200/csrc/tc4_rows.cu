@@ -84,57 +84,65 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-// 8 consecutive fp32 -> 8 bf16 hi (16 B) + 8 bf16 lo (16 B); element 0 at the lowest address
+// 4 consecutive fp32 -> 4 bf16 hi (8 B) + 4 bf16 lo (8 B); element 0 at the lowest address
+__device__ __forceinline__ void split4(const float4 a, uint2& hi, uint2& lo) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2bfloat162_rn(a.z - f1.x, a.w - f1.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
 __device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
-  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    const float2 hf = __bfloat1622float2(hh);
-    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
+  uint2 h0, l0, h1, l1;
+  split4(a, h0, l0);
+  split4(b, h1, l1);
+  hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
 }
 
-// One [128 rows][64 cols] fp32 slab in flight per CTA: thread `tid` owns the 16-byte bf16 chunk ch = tid & 7 of rows
-// (tid >> 3) + 32 i, i = 0..3 (two float4 loads each; a warp covers 4 rows x 256 B -- fully coalesced).
+// One [128 rows][64 cols] fp32 slab in flight per CTA: thread `tid` owns float4 c4 = tid & 15 (columns 4 c4 .. 4 c4 + 3)
+// of rows (tid >> 4) + 16 i, i = 0..7 -- a warp reads two full 256-byte rows per instruction (fully coalesced).
 struct Slab {
   float4 v[8];
 };
-// columns of chunk ch: ch < 4 -> o0 + 8 ch, else o1 + 8 (ch - 4)  (two 32-column segments; o1 = o0 + 32 when contiguous)
-__device__ __forceinline__ void slab_load(Slab& s, const float* __restrict__ src, long long ld, int o0, int o1,
-                                          long long row0, long long M, int tid) {
-  const int ch = tid & 7;
-  const int col = (ch < 4) ? (o0 + ch * 8) : (o1 + (ch - 4) * 8);
+// q = address of the thread's float4 in its first row, step = 16 row strides, rows_left = valid rows from that row on
+__device__ __forceinline__ void slab_load(Slab& s, const float* __restrict__ q, long long step, int rows_left) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long gm = row0 + (tid >> 3) + 32 * i;
-    if (gm < M) {
-      const float4* q = reinterpret_cast<const float4*>(src + gm * ld + col);
-      s.v[2 * i] = __ldg(q);
-      s.v[2 * i + 1] = __ldg(q + 1);
+  for (int i = 0; i < 8; ++i) {
+    if (16 * i < rows_left) {
+      s.v[i] = __ldg(reinterpret_cast<const float4*>(q + i * step));
     } else {
-      s.v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      s.v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 }
-// split + store into a SWIZZLE_128B tile whose rows are the slab rows (128 B = 64 bf16 per row)
-__device__ __forceinline__ void slab_store(const Slab& s, unsigned char* hi, unsigned char* lo, bool single, int tid) {
-  const int ch = tid & 7;
+// split + store into a SWIZZLE_128B tile whose rows are the slab rows (128 B = 64 bf16 per row).  `hi` / `lo` already
+// include the thread's offset r0 * 128 + ((c4 / 2) ^ (r0 & 7)) * 16 + (c4 & 1) * 8; rows r0 + 16 i share r0's swizzle, so
+// the eight 8-byte stores use immediate offsets.  A warp writes two full rows per instruction (conflict-free).
+__device__ __forceinline__ void slab_store(const Slab& s, unsigned char* hi, unsigned char* lo, bool single) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = (tid >> 3) + 32 * i;
-    uint4 h, l;
-    split8(s.v[2 * i], s.v[2 * i + 1], h, l);
-    const int off = row * 128 + ((ch ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4*>(hi + off) = h;
-    if (!single) *reinterpret_cast<uint4*>(lo + off) = l;
+  for (int i = 0; i < 8; ++i) {
+    uint2 h, l;
+    split4(s.v[i], h, l);
+    *reinterpret_cast<uint2*>(hi + i * 2048) = h;
+    if (!single) *reinterpret_cast<uint2*>(lo + i * 2048) = l;
   }
+}
+__device__ __forceinline__ int slab_st_off(int tid) {
+  const int c4 = tid & 15, r0 = tid >> 4;
+  return r0 * 128 + (((c4 >> 1) ^ (r0 & 7)) << 4) + ((c4 & 1) << 3);
+}
+// running column sums of the slabs a thread has loaded (its 4 columns are the same in every slab)
+__device__ __forceinline__ void slab_colsum(const Slab& s, float (&c)[4]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c[0] += s.v[i].x; c[1] += s.v[i].y; c[2] += s.v[i].z; c[3] += s.v[i].w;
+  }
+}
+// one warp polls the mbarrier, everyone else parks on the CTA barrier (spinning threads would steal issue slots)
+__device__ __forceinline__ void cta_wait(uint32_t bar, uint32_t parity, int warp) {
+  if (warp == 0) mbar_wait(bar, parity);
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------ forward / dgrad
@@ -148,23 +156,24 @@ struct RowsP {
   float* Y;
   long long ldy;
   long long M;
-  int N, KB, flags, ntiles;
+  int flags, ntiles;
 };
 
-__global__ void __launch_bounds__(NT, 2) rows_gemm_kernel(const RowsP p) {
+template <int NB, int KB>
+__global__ void __launch_bounds__(NT, (NB == 1 && KB == 1) ? 3 : 2) rows_gemm_kernel(const RowsP p) {
+  constexpr int N = 64 * NB;
+  constexpr int WT = N * 128;                 // bytes of one K block of one W plane ([N rows][128 B])
+  constexpr uint32_t TCOLS = (NB == 1) ? 64u : ((NB == 2) ? 128u : 256u);
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) unsigned long long bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool single = (p.flags & F_BF16) != 0;
-  const int N = p.N, KB = p.KB;
-  const int wtile = N * 128;               // bytes of one K block of one W plane ([N rows][128 B])
   unsigned char* w_hi = smem;
-  unsigned char* w_lo = smem + KB * wtile;
-  unsigned char* a_hi = smem + 2 * KB * wtile;
+  unsigned char* w_lo = smem + KB * WT;
+  unsigned char* a_hi = smem + 2 * KB * WT;
   unsigned char* a_lo = a_hi + PLANE;
-  const uint32_t tmem_cols = (N <= 64) ? 64u : ((N <= 128) ? 128u : 256u);
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(NT, 2) rows_gemm_kernel(const RowsP p) {
   __syncwarp();
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"(tmem_cols)
+                 "r"(TCOLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(NT, 2) rows_gemm_kernel(const RowsP p) {
     }
     uint4 h, l;
     split8(a, b, h, l);
-    const int off = kb * wtile + n * 128 + ((ch ^ (n & 7)) << 4);
+    const int off = kb * WT + n * 128 + ((ch ^ (n & 7)) << 4);
     *reinterpret_cast<uint4*>(w_hi + off) = h;
     if (!single) *reinterpret_cast<uint4*>(w_lo + off) = l;
   }
@@ -203,28 +212,49 @@ __global__ void __launch_bounds__(NT, 2) rows_gemm_kernel(const RowsP p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t bar_a = smem_u32(&bar);
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(RB >> 4) << 24);
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(RB >> 4) << 24);
   const bool accum = (p.flags & F_ACCUM) != 0, relu = (p.flags & F_RELU) != 0;
+
+  // loader geometry (thread constants)
+  const int r0 = tid >> 4, col = (tid & 15) * 4;
+  const int st_off = slab_st_off(tid);
+  // epilogue geometry: warp = (TMEM lane group lg, 32-column half); the operand stage ([128 rows][2 halves][128 B])
+  // doubles as a warp-private transposition buffer, 16-byte chunk c of row r at chunk position c ^ (r & 7)
   const int lg = warp & 3, half = warp >> 2;
+  const int erow = lg * 32 + lane;
+  unsigned char* stw = a_hi + erow * 256 + half * 128;
+  const int swz = (erow & 7) << 4;
+  const int rr = lane >> 3, cc = lane & 7;          // copy-out: rows lg*32 + 4 i + rr, float4 column cc
+  const unsigned char* str_e = a_hi + (lg * 32 + rr) * 256 + half * 128 + ((cc ^ rr) << 4);        // even i
+  const unsigned char* str_o = a_hi + (lg * 32 + rr) * 256 + half * 128 + ((cc ^ (rr + 4)) << 4);  // odd i
+  float4 bb[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+    bb[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + j * 64 + half * 32 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t tacc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * 32);
+  const long long ystep = 4 * p.ldy;
 
   Slab pre;
   int tile = blockIdx.x, kb = 0;
   uint32_t ph = 0;
   bool pending = false;
-  if (tile < p.ntiles) slab_load(pre, p.X0, p.ldx0, 0, 32, (long long)tile * RB, p.M, tid);
+  if (tile < p.ntiles) {
+    const long long row0 = (long long)tile * RB + r0;
+    slab_load(pre, p.X0 + row0 * p.ldx0 + col, 16 * p.ldx0, (int)min((long long)RB, p.M - row0));
+  }
   while (tile < p.ntiles) {
-    if (pending) {               // MMAs of the previous K block still read the stage
-      mbar_wait(bar_a, ph);
+    if (KB > 1 && pending) {     // MMAs of the previous K block still read the stage
+      cta_wait(bar_a, ph, warp);
       ph ^= 1;
       pending = false;
     }
-    slab_store(pre, a_hi, a_lo, single, tid);
+    slab_store(pre, a_hi + st_off, a_lo + st_off, single);
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
       const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
-      const uint32_t bh = smem_u32(w_hi) + (uint32_t)(kb * wtile), bl = smem_u32(w_lo) + (uint32_t)(kb * wtile);
+      const uint32_t bh = smem_u32(w_hi) + (uint32_t)(kb * WT), bl = smem_u32(w_lo) + (uint32_t)(kb * WT);
 #pragma unroll
       for (int k16 = 0; k16 < 4; ++k16) {
         const uint32_t ko = k16 * 32;   // 16 bf16 along K inside the 128-byte swizzle atom
@@ -249,44 +279,38 @@ __global__ void __launch_bounds__(NT, 2) rows_gemm_kernel(const RowsP p) {
       ntile = tile + gridDim.x;
     }
     if (ntile < p.ntiles) {
-      const float* xs = (nkb == 0) ? p.X0 : ((nkb == 1) ? p.X1 : p.X2);
-      const long long ls = (nkb == 0) ? p.ldx0 : ((nkb == 1) ? p.ldx1 : p.ldx2);
-      slab_load(pre, xs, ls, 0, 32, (long long)ntile * RB, p.M, tid);
+      const float* xs = (KB == 1 || nkb == 0) ? p.X0 : ((nkb == 1) ? p.X1 : p.X2);
+      const long long ls = (KB == 1 || nkb == 0) ? p.ldx0 : ((nkb == 1) ? p.ldx1 : p.ldx2);
+      const long long row0 = (long long)ntile * RB + r0;
+      slab_load(pre, xs + row0 * ls + col, 16 * ls, (int)min((long long)RB, p.M - row0));
     }
     if (kb == KB - 1) {
-      mbar_wait(bar_a, ph);
+      cta_wait(bar_a, ph, warp);
       ph ^= 1;
       pending = false;
       tc_fence_after();
-      // epilogue: the stage (32 KB = [128 rows][2 halves][128 B]) doubles as a warp-private transposition buffer
-      const int row = lg * 32 + lane;
-      unsigned char* stg = a_hi;
-      for (int j = 0; j * 64 < N; ++j) {
-        const int col0 = j * 64 + half * 32;
+      const long long erow0 = (long long)tile * RB + lg * 32 + rr;
+      const int rows_left = (int)min((long long)RB, p.M - erow0);
+      float* yrow = p.Y + erow0 * p.ldy + half * 32 + cc * 4;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
 #pragma unroll
         for (int c16 = 0; c16 < 2; ++c16) {
           uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(col0 + 16 * c16), v);
+          tmem_ld16(tacc + (uint32_t)(j * 64 + 16 * c16), v);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = 4 * c16 + q;
-            float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                   __uint_as_float(v[4 * q + 3]));
-            if (p.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * c));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            *reinterpret_cast<float4*>(stg + row * 256 + half * 128 + ((c ^ (row & 7)) << 4)) = o;
-          }
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(stw + ((((4 * c16 + q) << 4)) ^ swz)) =
+                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                            __uint_as_float(v[4 * q + 3]));
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int r = lg * 32 + 4 * i + (lane >> 3), c = lane & 7;
-          float4 o = *reinterpret_cast<const float4*>(stg + r * 256 + half * 128 + ((c ^ (r & 7)) << 4));
-          const long long gm = (long long)tile * RB + r;
-          if (gm < p.M) {
-            float4* dst = reinterpret_cast<float4*>(p.Y + gm * p.ldy + col0 + 4 * c);
+          float4 o = *reinterpret_cast<const float4*>(((i & 1) ? str_o : str_e) + i * 1024);
+          o.x += bb[j].x; o.y += bb[j].y; o.z += bb[j].z; o.w += bb[j].w;
+          if (4 * i < rows_left) {
+            float4* dst = reinterpret_cast<float4*>(yrow + i * ystep + j * 64);
             if (accum) {
               const float4 old = *dst;
               o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
@@ -308,7 +332,7 @@ __global__ void __launch_bounds__(NT, 2) rows_gemm_kernel(const RowsP p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
   }
 }
 
@@ -319,7 +343,6 @@ struct WgP {
   int a_off0, a_off1;
   const float *B0, *B1, *B2;   // NB slabs of 64 columns
   long long ldb0, ldb1, ldb2;
-  int NB;
   long long M;
   int nblk;
   float* partial;              // [gridDim.x][WG_PART]
@@ -327,7 +350,9 @@ struct WgP {
   int flags;
 };
 
-__global__ void __launch_bounds__(NT, 2) rows_wgrad_kernel(const WgP p) {
+template <int NB>
+__global__ void __launch_bounds__(NT, (NB == 3) ? 2 : 3) rows_wgrad_kernel(const WgP p) {
+  constexpr uint32_t TCOLS = (NB == 1) ? 64u : ((NB == 2) ? 128u : 256u);
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) unsigned long long bar;
@@ -335,11 +360,13 @@ __global__ void __launch_bounds__(NT, 2) rows_wgrad_kernel(const WgP p) {
   __shared__ float red[WG_LD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool single = (p.flags & F_BF16) != 0;
-  // A: two 64-channel MN blocks per plane (the MMA's M is 128; block 1 is zero padding), B: one block per plane
+  // [A hi][A lo][B hi][B lo], one 64-channel MN block each.  The MMA's M is 128: the second 64-channel block of the A
+  // descriptors (leading-dimension byte offset = PLANE) aliases the NEXT plane -- finite bf16 data whose products land
+  // in accumulator rows 64..127, which are never read.
   unsigned char* a_hi = smem;
-  unsigned char* a_lo = smem + 2 * PLANE;
-  unsigned char* b_hi = smem + 4 * PLANE;
-  unsigned char* b_lo = smem + 5 * PLANE;
+  unsigned char* a_lo = smem + PLANE;
+  unsigned char* b_hi = smem + 2 * PLANE;
+  unsigned char* b_lo = smem + 3 * PLANE;
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -348,14 +375,11 @@ __global__ void __launch_bounds__(NT, 2) rows_wgrad_kernel(const WgP p) {
   __syncwarp();
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"(256u)
+                 "r"(TCOLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < PLANE / 16; i += NT) {
-    *reinterpret_cast<uint4*>(a_hi + PLANE + i * 16) = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(a_lo + PLANE + i * 16) = make_uint4(0u, 0u, 0u, 0u);
-  }
+  for (int i = tid; i < 4 * PLANE / 16; i += NT) *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < WG_LD; i += NT) red[i] = 0.f;
   tc_fence_before();
   __syncthreads();
@@ -363,112 +387,98 @@ __global__ void __launch_bounds__(NT, 2) rows_wgrad_kernel(const WgP p) {
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t bar_a = smem_u32(&bar);
   // M = 128, N = 64, A and B MN-major (bits 15, 16)
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
-                         ((uint32_t)(128 >> 4) << 24);
-  const int NB = p.NB;
-  float cs[3][8];
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+  float cs[NB][4];
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
+  for (int j = 0; j < NB; ++j)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) cs[j][q] = 0.f;
+    for (int q = 0; q < 4; ++q) cs[j][q] = 0.f;
 
+  const int r0 = tid >> 4, c4 = tid & 15;
+  const int st_off = slab_st_off(tid);
+  const int acol = (c4 < 8) ? (p.a_off0 + c4 * 4) : (p.a_off1 + (c4 - 8) * 4);
   Slab pre;
   uint32_t ph = 0;
   bool pending = false;
-  int blk = blockIdx.x;
   bool first = true;
-  if (blk < p.nblk) slab_load(pre, p.A, p.lda, p.a_off0, p.a_off1, (long long)blk * RB, p.M, tid);
+  int blk = blockIdx.x;
+  if (blk < p.nblk) {
+    const long long row0 = (long long)blk * RB + r0;
+    slab_load(pre, p.A + row0 * p.lda + acol, 16 * p.lda, (int)min((long long)RB, p.M - row0));
+  }
   while (blk < p.nblk) {
     const int nblk_next = blk + gridDim.x;
+    const long long row0 = (long long)blk * RB + r0;
+    const int rows_left = (int)min((long long)RB, p.M - row0);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      if (s <= NB) {
-        if (pending) {           // the previous MMA group still reads A / B
-          mbar_wait(bar_a, ph);
-          ph ^= 1;
-          pending = false;
-        }
-        if (s == 0) {
-          slab_store(pre, a_hi, a_lo, single, tid);
-          if (p.colsum_src == 1) {
+    for (int s = 0; s <= NB; ++s) {
+      if (pending) {           // the previous MMA group still reads A / B
+        cta_wait(bar_a, ph, warp);
+        ph ^= 1;
+        pending = false;
+      }
+      if (s == 0) {
+        slab_store(pre, a_hi + st_off, a_lo + st_off, single);
+        if (p.colsum_src == 1) slab_colsum(pre, cs[0]);
+      } else {
+        slab_store(pre, b_hi + st_off, b_lo + st_off, single);
+        if (p.colsum_src == 2) slab_colsum(pre, cs[(s > 0) ? (s - 1) : 0]);
+      }
+      fence_proxy_async();
+      __syncthreads();
+      // prefetch the next slab: B_s of this block, or A of the CTA's next block
+      if (s < NB) {
+        const float* bs = (s == 0) ? p.B0 : ((s == 1) ? p.B1 : p.B2);
+        const long long ls = (s == 0) ? p.ldb0 : ((s == 1) ? p.ldb1 : p.ldb2);
+        slab_load(pre, bs + row0 * ls + c4 * 4, 16 * ls, rows_left);
+      } else if (nblk_next < p.nblk) {
+        const long long nrow0 = (long long)nblk_next * RB + r0;
+        slab_load(pre, p.A + nrow0 * p.lda + acol, 16 * p.lda, (int)min((long long)RB, p.M - nrow0));
+      }
+      if (s >= 1) {
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+          const uint32_t tm = tmem_base + (uint32_t)((s - 1) * 64);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              cs[0][0] += pre.v[2 * i].x; cs[0][1] += pre.v[2 * i].y; cs[0][2] += pre.v[2 * i].z; cs[0][3] += pre.v[2 * i].w;
-              cs[0][4] += pre.v[2 * i + 1].x; cs[0][5] += pre.v[2 * i + 1].y; cs[0][6] += pre.v[2 * i + 1].z;
-              cs[0][7] += pre.v[2 * i + 1].w;
+          for (int k16 = 0; k16 < 8; ++k16) {
+            const uint32_t ko = k16 * 2048;   // 16 pixel rows = two 8-row groups of 1024 B
+            const uint64_t dah = make_desc(ah + ko, PLANE, 1024), dal = make_desc(al + ko, PLANE, 1024);
+            const uint64_t dbh = make_desc(bh + ko, PLANE, 1024), dbl = make_desc(bl + ko, PLANE, 1024);
+            const uint32_t acc = (!first || k16 > 0) ? 1u : 0u;
+            if (!single) {
+              umma_bf16(tm, dal, dbh, idesc, acc);
+              umma_bf16(tm, dah, dbl, idesc, 1u);
+              umma_bf16(tm, dah, dbh, idesc, 1u);
+            } else {
+              umma_bf16(tm, dah, dbh, idesc, acc);
             }
           }
-        } else {
-          slab_store(pre, b_hi, b_lo, single, tid);
-          if (p.colsum_src == 2) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float* c = cs[(s > 0) ? (s - 1) : 0];
-              c[0] += pre.v[2 * i].x; c[1] += pre.v[2 * i].y; c[2] += pre.v[2 * i].z; c[3] += pre.v[2 * i].w;
-              c[4] += pre.v[2 * i + 1].x; c[5] += pre.v[2 * i + 1].y; c[6] += pre.v[2 * i + 1].z;
-              c[7] += pre.v[2 * i + 1].w;
-            }
-          }
+          umma_commit(bar_a);
         }
-        fence_proxy_async();
-        __syncthreads();
-        // prefetch the next slab: B_s of this block, or A of the CTA's next block
-        if (s < NB) {
-          const float* bs = (s == 0) ? p.B0 : ((s == 1) ? p.B1 : p.B2);
-          const long long ls = (s == 0) ? p.ldb0 : ((s == 1) ? p.ldb1 : p.ldb2);
-          slab_load(pre, bs, ls, 0, 32, (long long)blk * RB, p.M, tid);
-        } else if (nblk_next < p.nblk) {
-          slab_load(pre, p.A, p.lda, p.a_off0, p.a_off1, (long long)nblk_next * RB, p.M, tid);
-        }
-        if (s >= 1) {
-          if (tid == 0) {
-            tc_fence_after();
-            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-            const uint32_t tm = tmem_base + (uint32_t)((s - 1) * 64);
-#pragma unroll
-            for (int k16 = 0; k16 < 8; ++k16) {
-              const uint32_t ko = k16 * 2048;   // 16 pixel rows = two 8-row groups of 1024 B
-              const uint64_t dah = make_desc(ah + ko, PLANE, 1024), dal = make_desc(al + ko, PLANE, 1024);
-              const uint64_t dbh = make_desc(bh + ko, PLANE, 1024), dbl = make_desc(bl + ko, PLANE, 1024);
-              const uint32_t acc = (!first || k16 > 0) ? 1u : 0u;
-              if (!single) {
-                umma_bf16(tm, dal, dbh, idesc, acc);
-                umma_bf16(tm, dah, dbl, idesc, 1u);
-                umma_bf16(tm, dah, dbh, idesc, 1u);
-              } else {
-                umma_bf16(tm, dah, dbh, idesc, acc);
-              }
-            }
-            umma_commit(bar_a);
-          }
-          pending = true;
-        }
+        pending = true;
       }
     }
     first = false;
     blk = nblk_next;
   }
   if (pending) {
-    mbar_wait(bar_a, ph);
+    cta_wait(bar_a, ph, warp);
     ph ^= 1;
   }
   tc_fence_after();
   float* part = p.partial + (long long)blockIdx.x * WG_PART;
   const int lg = warp & 3, half = warp >> 2;
-  const bool any = blockIdx.x < p.nblk;
-  if (lg < 2) {                      // D rows 64..127 belong to the zero half of A
+  if (lg < 2) {                      // accumulator rows 64..127 are padding
     const int row = lg * 32 + lane;
+#pragma unroll
     for (int j = 0; j < NB; ++j) {
 #pragma unroll
       for (int c16 = 0; c16 < 2; ++c16) {
         uint32_t v[16];
         const int col0 = j * 64 + half * 32 + c16 * 16;
-        if (any) {
-          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)col0, v);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = 0u;
-        }
+        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)col0, v);
         float4* dst = reinterpret_cast<float4*>(part + row * WG_LD + col0);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -478,53 +488,49 @@ __global__ void __launch_bounds__(NT, 2) rows_wgrad_kernel(const WgP p) {
     }
   }
   if (p.colsum_src) {
-    const int ch = tid & 7;
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
+    for (int j = 0; j < NB; ++j)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int o = ch * 8 + q;
-        if (j < ((p.colsum_src == 1) ? 1 : NB)) atomicAdd(&red[j * 64 + o], cs[j][q]);
-      }
+      for (int q = 0; q < 4; ++q)
+        if (j == 0 || p.colsum_src == 2) atomicAdd(&red[j * 64 + c4 * 4 + q], cs[j][q]);
     __syncthreads();
     for (int i = tid; i < WG_LD; i += NT) part[64 * WG_LD + i] = red[i];
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
   }
 }
 
-// out[b][i][j] = sum_parts D[b rb + (T ? j : i)][b cb + (T ? i : j)];  dbias[n] = sum_parts colsum[n]
-__global__ void rows_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ out, int nb,
-                                         int ni, int nj, int T, int rb, int cb, float* __restrict__ dbias, int nbias) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = nb * ni * nj;
-  long long src;
-  float* dst;
-  if (idx < total) {
-    const int b = idx / (ni * nj), rem = idx - b * ni * nj;
-    const int i = rem / nj, j = rem - i * nj;
-    const int r = b * rb + (T ? j : i), c = b * cb + (T ? i : j);
-    src = (long long)r * WG_LD + c;
-    dst = out + idx;
-  } else if (idx - total < nbias) {
-    src = 64LL * WG_LD + (idx - total);
-    dst = dbias + (idx - total);
-  } else {
+// D[r][c] = sum over the per-CTA partial tiles (coalesced reads, 4 part groups per element, fixed summation order),
+// then scattered to out[b][i][j] with D[b rb + (T ? j : i)][b cb + (T ? i : j)];  rows >= 64 of the index space are the
+// column sums -> dbias
+__global__ void __launch_bounds__(256) rows_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts,
+                                                               float* __restrict__ out, int nb, int ni, int nj, int T,
+                                                               int rb, int cb, float* __restrict__ dbias, int nbias,
+                                                               int ncols) {
+  __shared__ float sm[4][64];
+  const int e = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int row = blockIdx.x / 3, c = (blockIdx.x % 3) * 64 + e;       // row 64 = the column sums
+  float a = 0.f;
+  if (c < ncols) {
+    const float* src = partial + (long long)row * WG_LD + c;
+    for (int q = g; q < nparts; q += 4) a += src[(long long)q * WG_PART];
+  }
+  sm[g][e] = a;
+  __syncthreads();
+  if (g != 0 || c >= ncols) return;
+  a = (sm[0][e] + sm[1][e]) + (sm[2][e] + sm[3][e]);
+  if (row == 64) {
+    if (c < nbias) dbias[c] = a;
     return;
   }
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int c = 0;
-  for (; c + 3 < nparts; c += 4) {
-    a0 += partial[(long long)c * WG_PART + src];
-    a1 += partial[(long long)(c + 1) * WG_PART + src];
-    a2 += partial[(long long)(c + 2) * WG_PART + src];
-    a3 += partial[(long long)(c + 3) * WG_PART + src];
+  for (int b = 0; b < nb; ++b) {
+    const int rr = row - b * rb, cc = c - b * cb;
+    const int i = T ? cc : rr, j = T ? rr : cc;
+    if (i >= 0 && i < ni && j >= 0 && j < nj) out[((long long)b * ni + i) * nj + j] = a;
   }
-  for (; c < nparts; ++c) a0 += partial[(long long)c * WG_PART + src];
-  *dst = (a0 + a1) + (a2 + a3);
 }
 
 static int num_sms() {
@@ -534,6 +540,26 @@ static int num_sms() {
 }
 static bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+template <int NB, int KB>
+static int launch_rows_gemm(const RowsP& p, cudaStream_t st) {
+  const int smem = 2 * KB * NB * 64 * 128 + 2 * PLANE + 1024;
+  int grid = ((NB == 1 && KB == 1) ? 3 : 2) * num_sms();
+  if (grid > p.ntiles) grid = p.ntiles;
+  TATT_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<NB, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  rows_gemm_kernel<NB, KB><<<grid, NT, smem, st>>>(p);
+  TATT_LAUNCH_CHECK("rows_gemm_kernel");
+  return 0;
+}
+template <int NB>
+static int launch_rows_wgrad(const WgP& p, int grid, cudaStream_t st) {
+  const int smem = 4 * PLANE + 1024;
+  TATT_CUDA(cudaFuncSetAttribute(rows_wgrad_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  rows_wgrad_kernel<NB><<<grid, NT, smem, st>>>(p);
+  TATT_LAUNCH_CHECK("rows_wgrad_kernel");
+  return 0;
+}
+constexpr int WG_MAX_GRID = 3 * 148;
+
 }  // namespace
 
 extern "C" {
@@ -541,7 +567,7 @@ extern "C" {
 int tatt_rows_gemm(const float* X0, long long ldx0, const float* X1, long long ldx1, const float* X2, long long ldx2,
                    const float* W, long long ldw, int wtrans, const float* bias, float* Y, long long ldy, long long M,
                    int N, int KB, int flags, void* stream) {
-  TATT_REQUIRE(M >= 1 && (N == 64 || N == 128 || N == 192) && KB >= 1 && KB <= 3 && KB * N <= 192,
+  TATT_REQUIRE(M >= 1 && (N == 64 || N == 128 || N == 192) && KB >= 1 && KB <= 3 && (KB == 1 || N == 64),
                "tatt_rows_gemm: unsupported shape M=%lld N=%d K=%d", M, N, 64 * KB);
   TATT_REQUIRE(X0 && W && Y && (KB < 2 || X1) && (KB < 3 || X2), "tatt_rows_gemm: null operand");
   TATT_REQUIRE(al16(X0) && al16(X1) && al16(X2) && al16(Y) && al16(bias) && (wtrans || al16(W)) && ldx0 % 4 == 0 &&
@@ -552,18 +578,19 @@ int tatt_rows_gemm(const float* X0, long long ldx0, const float* X1, long long l
   p.ldx0 = ldx0; p.ldx1 = ldx1; p.ldx2 = ldx2;
   p.W = W; p.ldw = ldw; p.wtrans = wtrans;
   p.bias = bias; p.Y = Y; p.ldy = ldy;
-  p.M = M; p.N = N; p.KB = KB; p.flags = flags;
+  p.M = M; p.flags = flags;
   p.ntiles = (int)((M + RB - 1) / RB);
-  const int smem = 2 * KB * N * 128 + 2 * PLANE + 1024;
-  int grid = 2 * num_sms();
-  if (grid > p.ntiles) grid = p.ntiles;
-  TATT_CUDA(cudaFuncSetAttribute(rows_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  rows_gemm_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(p);
-  TATT_LAUNCH_CHECK("rows_gemm_kernel");
-  return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (KB == 1) {
+    if (N == 64) return launch_rows_gemm<1, 1>(p, st);
+    if (N == 128) return launch_rows_gemm<2, 1>(p, st);
+    return launch_rows_gemm<3, 1>(p, st);
+  }
+  if (KB == 2) return launch_rows_gemm<1, 2>(p, st);
+  return launch_rows_gemm<1, 3>(p, st);
 }
 
-int tatt_rows_wgrad_ws_bytes(void) { return 2 * 148 * WG_PART * (int)sizeof(float) + 256; }
+int tatt_rows_wgrad_ws_bytes(void) { return WG_MAX_GRID * WG_PART * (int)sizeof(float) + 256; }
 
 int tatt_rows_wgrad(const float* A, long long lda, int a_off0, int a_off1, const float* B0, long long ldb0,
                     const float* B1, long long ldb1, const float* B2, long long ldb2, int NB, long long M,
@@ -574,7 +601,8 @@ int tatt_rows_wgrad(const float* A, long long lda, int a_off0, int a_off1, const
   TATT_REQUIRE(al16(A) && al16(B0) && al16(B1) && al16(B2) && al16(ws) && lda % 4 == 0 && ldb0 % 4 == 0 &&
                    ldb1 % 4 == 0 && ldb2 % 4 == 0 && a_off0 % 4 == 0 && a_off1 % 4 == 0,
                "tatt_rows_wgrad: operands must be 16-byte aligned with strides / offsets that are multiples of 4");
-  TATT_REQUIRE(colsum_src >= 0 && colsum_src <= 2 && (colsum_src == 0 || dbias) && nbias >= 0 && nbias <= WG_LD,
+  TATT_REQUIRE(colsum_src >= 0 && colsum_src <= 2 && (colsum_src == 0 || dbias) && nbias >= 0 &&
+                   nbias <= ((colsum_src == 1) ? 64 : 64 * NB),
                "tatt_rows_wgrad: bad column-sum request");
   {
     const int rmax = (nb - 1) * rb + (transpose ? nj : ni), cmax = (nb - 1) * cb + (transpose ? ni : nj);
@@ -585,23 +613,22 @@ int tatt_rows_wgrad(const float* A, long long lda, int a_off0, int a_off1, const
   p.A = A; p.lda = lda; p.a_off0 = a_off0; p.a_off1 = a_off1;
   p.B0 = B0; p.B1 = B1; p.B2 = B2;
   p.ldb0 = ldb0; p.ldb1 = ldb1; p.ldb2 = ldb2;
-  p.NB = NB; p.M = M;
+  p.M = M;
   p.nblk = (int)((M + RB - 1) / RB);
   p.colsum_src = colsum_src; p.flags = flags;
-  int grid = 2 * num_sms();
-  if (grid > 2 * 148) grid = 2 * 148;
+  int grid = ((NB == 3) ? 2 : 3) * num_sms();
+  if (grid > WG_MAX_GRID) grid = WG_MAX_GRID;
   if (grid > p.nblk) grid = p.nblk;
   TATT_REQUIRE((long long)grid * WG_PART * (long long)sizeof(float) <= ws_bytes,
                "tatt_rows_wgrad: workspace too small (%lld bytes, need %lld)", ws_bytes,
                (long long)grid * WG_PART * (long long)sizeof(float));
   p.partial = reinterpret_cast<float*>(ws);
-  const int smem = 6 * PLANE + 1024;
-  TATT_CUDA(cudaFuncSetAttribute(rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  rows_wgrad_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(p);
-  TATT_LAUNCH_CHECK("rows_wgrad_kernel");
-  const int total = nb * ni * nj + (colsum_src ? nbias : 0);
-  rows_wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      p.partial, grid, out, nb, ni, nj, transpose, rb, cb, dbias, colsum_src ? nbias : 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = (NB == 1) ? launch_rows_wgrad<1>(p, grid, st) : ((NB == 2) ? launch_rows_wgrad<2>(p, grid, st)
+                                                                     : launch_rows_wgrad<3>(p, grid, st));
+  if (rc) return rc;
+  rows_wgrad_reduce_kernel<<<(64 + (colsum_src ? 1 : 0)) * 3, 256, 0, st>>>(
+      p.partial, grid, out, nb, ni, nj, transpose, rb, cb, dbias, colsum_src ? nbias : 0, 64 * NB);
   TATT_LAUNCH_CHECK("rows_wgrad_reduce_kernel");
   return 0;
 }
