@@ -75,35 +75,42 @@ __global__ void prelu_bwd_kernel(const float* __restrict__ x, const float* __res
 }
 
 // in [N][H][W][4*C] -> out [N][2H][2W][C], out[n,2h+i,2w+j,c] = mish(in[n,h,w,4c+2i+j])
-__global__ void pixshuf_mish_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix_out,
-                                        int H2, int W2, int C) {
-  long long n = npix_out * C;
+// One thread per input float4 = the four sub-pixels (i,j) of channel c: the read is a coalesced float4, the four scalar
+// writes of C consecutive threads are four contiguous C-float runs (one per output pixel).
+__global__ void pixshuf_mish_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix_in,
+                                        int H, int W, int C) {
+  const long long n = npix_in * C;
+  const long long orow = 2LL * W * C;          // one output row
   GRID_STRIDE(i, n) {
-    int c = (int)(i % C);
-    long long p = i / C;
-    int ox = (int)(p % W2);
-    long long q = p / W2;
-    int oy = (int)(q % H2);
-    long long img = q / H2;
-    int h = oy >> 1, ii = oy & 1, w = ox >> 1, jj = ox & 1;
-    long long src = (((img * (H2 >> 1) + h) * (W2 >> 1) + w) * (4LL * C)) + 4 * c + 2 * ii + jj;
-    out[i] = mish_f(in[src]);
+    const int c = (int)(i % C);
+    const long long p = i / C;                 // input pixel (img, h, w)
+    const int w = (int)(p % W);
+    const long long q = p / W;                 // img * H + h
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    float* o = out + (2 * q) * orow + (2LL * w) * C + c;
+    o[0] = mish_f(v.x);
+    o[C] = mish_f(v.y);
+    o[orow] = mish_f(v.z);
+    o[orow + C] = mish_f(v.w);
   }
 }
 __global__ void pixshuf_mish_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout,
                                         float* __restrict__ din, long long npix_in, int H, int W, int C) {
-  // one thread per input element (coalesced on the 4C axis)
-  long long n = npix_in * 4LL * C;
+  const long long n = npix_in * C;
+  const long long orow = 2LL * W * C;
   GRID_STRIDE(i, n) {
-    int ch = (int)(i % (4 * C));
-    long long p = i / (4 * C);
-    int w = (int)(p % W);
-    long long q = p / W;
-    int h = (int)(q % H);
-    long long img = q / H;
-    int c = ch >> 2, ii = (ch >> 1) & 1, jj = ch & 1;
-    long long dst = (((img * (2 * H) + 2 * h + ii) * (2LL * W) + 2 * w + jj) * C) + c;
-    din[i] = dout[dst] * mish_grad(in[i]);
+    const int c = (int)(i % C);
+    const long long p = i / C;
+    const int w = (int)(p % W);
+    const long long q = p / W;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    const float* g = dout + (2 * q) * orow + (2LL * w) * C + c;
+    float4 r;
+    r.x = __ldg(g) * mish_grad(v.x);
+    r.y = __ldg(g + C) * mish_grad(v.y);
+    r.z = __ldg(g + orow) * mish_grad(v.z);
+    r.w = __ldg(g + orow + C) * mish_grad(v.w);
+    reinterpret_cast<float4*>(din)[i] = r;
   }
 }
 
@@ -304,10 +311,9 @@ int tatt_prelu_bwd(const float* x, const float* w, const float* dy, float* dx, f
 }
 
 int tatt_pixshuf2_mish_fwd(const float* in, float* out, long long nimg, int H, int W, int C, void* stream) {
-  long long npix_out = nimg * 4LL * H * W;
-  if (npix_out <= 0) return 0;
-  pixshuf_mish_fwd_kernel<<<ew_blocks(npix_out * C), 256, 0, (cudaStream_t)stream>>>(in, out, npix_out, 2 * H,
-                                                                                     2 * W, C);
+  long long npix_in = nimg * (long long)H * W;
+  if (npix_in <= 0) return 0;
+  pixshuf_mish_fwd_kernel<<<ew_blocks(npix_in * C), 256, 0, (cudaStream_t)stream>>>(in, out, npix_in, H, W, C);
   TATT_LAUNCH_CHECK("pixshuf_mish_fwd_kernel");
   return 0;
 }
@@ -315,8 +321,7 @@ int tatt_pixshuf2_mish_bwd(const float* in, const float* dout, float* din, long 
                            void* stream) {
   long long npix_in = nimg * (long long)H * W;
   if (npix_in <= 0) return 0;
-  pixshuf_mish_bwd_kernel<<<ew_blocks(npix_in * 4 * C), 256, 0, (cudaStream_t)stream>>>(in, dout, din, npix_in, H,
-                                                                                        W, C);
+  pixshuf_mish_bwd_kernel<<<ew_blocks(npix_in * C), 256, 0, (cudaStream_t)stream>>>(in, dout, din, npix_in, H, W, C);
   TATT_LAUNCH_CHECK("pixshuf_mish_bwd_kernel");
   return 0;
 }

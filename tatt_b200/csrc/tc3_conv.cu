@@ -224,6 +224,245 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent variant
+// conv3x3_tma_kernel above runs one tile per CTA: 6.9 waves of {prologue, halo load, 216 MMAs, epilogue} that do not
+// overlap (ncu: tensor pipe 26 %).  The rolling-halo variant below is persistent (one CTA per SM walks down a column of
+// 2-row tiles) and keeps the tensor pipe fed:
+//   * the 4 halo rows live in a circular buffer of two row PAIRS; consecutive tiles share two rows, so each tile only
+//     loads its two NEW rows -- into the pair that went dead after the ky = 0, 1 taps of the previous tile, i.e. the
+//     load is issued two thirds through the previous tile's MMAs and waited for just before this tile's ky = 1 taps;
+//   * two 128-column TMEM accumulators: the epilogue of tile t overlaps the MMAs of tile t+1;
+//   * the weight-tap ring keeps streaming across tiles;
+//   * the MMA thread builds descriptors with one integer add each (row bases precomputed per tile).
+// A pair is padded to a multiple of 1024 bytes so the TMA box (2 rows) and the UMMA descriptors agree on the swizzle.
+constexpr int ROW_BYTES = HALO_W * 128;                       // 16640
+constexpr int PAIR_BYTES = ((2 * ROW_BYTES + 1023) / 1024) * 1024;   // 34816
+constexpr int RL_A_PLANE = 2 * PAIR_BYTES;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B descriptors from their low words (start address >> 4, LBO field 1); high word: SBO 1024 B,
+// version 1, layout type 2
+// warp-uniform variants: the WHOLE warp executes the surrounding (uniform) control flow and one elected lane issues, so
+// ptxas keeps descriptors / addresses in uniform registers instead of emitting a per-lane "waterfall" loop around
+// every UTCHMMA (which is what `if (lane == 0) { ... }` around the issue loop compiles to)
+__device__ __forceinline__ void umma_lo_elect(uint32_t tmem_c, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                              uint32_t acc) {
+  constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(acc), "r"(HI)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
+
+template <bool single>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                    float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long pair_full[2], pair_empty[2], w_full[NSTAGE], w_empty[NSTAGE], acc_full[2],
+      acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nyb = H / 2, nxt = W / TW;
+  const int t0 = (int)((long long)blockIdx.x * ntiles / gridDim.x);
+  const int t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
+  const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + RL_A_PLANE, b_ring = a_lo + RL_A_PLANE;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&pair_full[i]), 1);
+      mbar_init(smem_u32(&pair_empty[i]), 1);
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), 4);
+    }
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(smem_u32(&w_full[s]), 1);
+      mbar_init(smem_u32(&w_empty[s]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t pair_bytes = (single ? 1u : 2u) * (uint32_t)(2 * ROW_BYTES);
+      int nload0 = 0, nload1 = 0;                 // loads issued into pair 0 / 1
+      int ws = 0;                                 // weight ring stage
+      uint32_t wpar = 0;                          // parity of the NEXT wait on w_empty[ws] (valid once the ring wrapped)
+      bool wrapped = false;
+      for (int t = t0; t < t1; ++t) {
+        const int yb = t % nyb, xb = (t / nyb) % nxt, n = t / (nyb * nxt);
+        const int y0 = 2 * yb, x0 = xb * TW;
+        const bool fresh = (t == t0) || (yb == 0);
+        const int p0 = (y0 >> 1) & 1;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (k == 0 && !fresh) continue;          // rows y0-1, y0 are already there (previous tile's rows 2, 3)
+          const int pr = (k == 0) ? p0 : (p0 ^ 1);
+          const int nl = pr ? nload1 : nload0;
+          if (nl > 0) mbar_wait(smem_u32(&pair_empty[pr]), (uint32_t)((nl - 1) & 1));
+          const uint32_t bar = smem_u32(&pair_full[pr]);
+          mbar_expect_tx(bar, pair_bytes);
+          const int yy = (k == 0) ? (y0 - 1) : (y0 + 1);
+          tma_load_4d(a_hi + (uint32_t)(pr * PAIR_BYTES), &tmAh, bar, 0, x0 - 1, yy, n);
+          if (!single) tma_load_4d(a_lo + (uint32_t)(pr * PAIR_BYTES), &tmAl, bar, 0, x0 - 1, yy, n);
+          if (pr) ++nload1; else ++nload0;
+        }
+        for (int tap = 0; tap < 9; ++tap) {
+          if (wrapped) mbar_wait(smem_u32(&w_empty[ws]), wpar);
+          const uint32_t dst = b_ring + (uint32_t)(ws * B_TAP_BYTES);
+          mbar_expect_tx(smem_u32(&w_full[ws]), (uint32_t)(single ? B_TAP_BYTES / 2 : B_TAP_BYTES));
+          tma_load_2d(dst, &tmBh, smem_u32(&w_full[ws]), tap * 64, 0);
+          if (!single) tma_load_2d(dst + 64 * 128, &tmBl, smem_u32(&w_full[ws]), tap * 64, 0);
+          if (++ws == NSTAGE) {
+            ws = 0;
+            if (wrapped) wpar ^= 1;
+            wrapped = true;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    {                                             // whole warp, uniform control flow; one elected lane issues
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t LBO1 = 1u << 16;
+      int nfull0 = 0, nfull1 = 0;                 // pair loads consumed
+      int ws = 0;
+      uint32_t wpar = 0;
+      int it = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int yb = t % nyb;
+        const int y0 = 2 * yb;
+        const bool fresh = (t == t0) || (yb == 0);
+        const bool next_fresh = (t + 1 < t1) && (((t + 1) % nyb) == 0);
+        const int p0 = (y0 >> 1) & 1, p1 = p0 ^ 1;
+        if (it >= 2) mbar_wait(smem_u32(&acc_empty[it & 1]), (uint32_t)(((it >> 1) - 1) & 1));
+        if (fresh) {
+          mbar_wait(smem_u32(&pair_full[p0]), (uint32_t)((p0 ? nfull1 : nfull0) & 1));
+          if (p0) ++nfull1; else ++nfull0;
+        }
+        // halo row j (0..3) of this tile lives in circular slot (y0 + j) & 3 = pair (slot >> 1), row (slot & 1)
+        uint32_t rowh[4], rowl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int slot = (y0 + j) & 3;
+          const uint32_t off = (uint32_t)((slot >> 1) * PAIR_BYTES + (slot & 1) * ROW_BYTES);
+          rowh[j] = ((a_hi + off) >> 4) | LBO1;
+          rowl[j] = ((a_lo + off) >> 4) | LBO1;
+        }
+        const uint32_t tacc = tmem_base + (uint32_t)((it & 1) * 128);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap % 3;
+          if (tap == 3) {                          // rows 2, 3 (the pair loaded for this tile) are first touched here
+            mbar_wait(smem_u32(&pair_full[p1]), (uint32_t)((p1 ? nfull1 : nfull0) & 1));
+            if (p1) ++nfull1; else ++nfull0;
+          }
+          mbar_wait(smem_u32(&w_full[ws]), wpar);
+          tc_fence_after();
+          const uint32_t bh = ((b_ring + (uint32_t)(ws * B_TAP_BYTES)) >> 4) | LBO1, bl = bh + ((64 * 128) >> 4);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const uint32_t ah = rowh[r + ky] + (uint32_t)(kx * 8), al = rowl[r + ky] + (uint32_t)(kx * 8);
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+              const uint32_t acc = (tap > 0 || k16 > 0) ? 1u : 0u;
+              if (!single) {
+                umma_lo_elect(tacc + (uint32_t)(r * 64), al + 2 * k16, bh + 2 * k16, idesc, acc);
+                umma_lo_elect(tacc + (uint32_t)(r * 64), ah + 2 * k16, bl + 2 * k16, idesc, 1u);
+                umma_lo_elect(tacc + (uint32_t)(r * 64), ah + 2 * k16, bh + 2 * k16, idesc, 1u);
+              } else {
+                umma_lo_elect(tacc + (uint32_t)(r * 64), ah + 2 * k16, bh + 2 * k16, idesc, acc);
+              }
+            }
+          }
+          umma_commit_elect(smem_u32(&w_empty[ws]));
+          if (++ws == NSTAGE) {
+            ws = 0;
+            wpar ^= 1;
+          }
+          if (tap == 5) umma_commit_elect(smem_u32(&pair_empty[p0]));   // rows 0, 1 are dead: the next tile's new rows go here
+        }
+        if (next_fresh) umma_commit_elect(smem_u32(&pair_empty[p1]));   // the next tile reloads both pairs
+        umma_commit_elect(smem_u32(&acc_full[it & 1]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
+    const int lg = warp & 3;
+    int it = 0;
+    for (int t = t0; t < t1; ++t, ++it) {
+      const int yb = t % nyb, xb = (t / nyb) % nxt, n = t / (nyb * nxt);
+      const int y0 = 2 * yb, px = xb * TW + lg * 32 + lane;
+      mbar_wait(smem_u32(&acc_full[it & 1]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float* dst = Y + (((long long)n * H + (y0 + r)) * W + px) * 64;
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((it & 1) * 128 + r * 64 + c16 * 16), v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o;
+            o.x = __uint_as_float(v[4 * q + 0]);
+            o.y = __uint_as_float(v[4 * q + 1]);
+            o.z = __uint_as_float(v[4 * q + 2]);
+            o.w = __uint_as_float(v[4 * q + 3]);
+            if (bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c16 * 16 + 4 * q));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(dst + c16 * 16 + 4 * q) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[it & 1]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dWt[(tap,ci)][co] += sum_px X[px + tap][ci] * dY[px][co]  for the same 3x3 / 64->64 conv.  The reduction axis is the
 // pixel axis, so both operands are MN-major tiles whose rows are pixels (128 B = 64 bf16 channels).  One k-tile =
@@ -399,9 +638,9 @@ static inline long long rup8(long long x) { return (x + 7) & ~7LL; }
 // conv3x3 64->64 through the TMA kernel.  Returns 0 ok, 1 error, -1 not eligible (caller falls through).
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
                             int single, void* ws, long long ws_bytes, cudaStream_t st) {
-  static const int mode = []() {          // TATT_TMA: 0 = off, 1 = on (base_offset 0), 2 = on (base_offset from address)
-    const char* e = getenv("TATT_TMA");
-    return e ? atoi(e) : 1;
+  static const int mode = []() {          // TATT_TMA: 0 = off, 1 / 2 = one tile per CTA (base_offset 0 / from address),
+    const char* e = getenv("TATT_TMA");   //           3 = persistent rolling-halo kernel (default)
+    return e ? atoi(e) : 3;
   }();
   if (mode == 0 || ws == nullptr || W % TW != 0 || H % 2 != 0) return -1;
   EncodeTiledFn enc = get_encode();
@@ -421,7 +660,7 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
   {
     cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
     cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
-    cuuint32_t box[4] = {64, HALO_W, R + 2, 1};
+    cuuint32_t box[4] = {64, HALO_W, (cuuint32_t)(mode == 3 ? 2 : R + 2), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     for (int pl = 0; pl < 2; ++pl) {
       CUresult r = enc(pl ? &tmAl : &tmAh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, pl ? (void*)Alo : (void*)Ahi, gdim, gstr,
@@ -441,6 +680,22 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return tatt_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
+  }
+  if (mode == 3) {
+    const int smem = 2 * RL_A_PLANE + NSTAGE * B_TAP_BYTES + 1024;
+    const int ntiles = nimg * (H / 2) * (W / TW);
+    int dev = 0, nsm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = ntiles < nsm ? ntiles : nsm;
+    if (single) {
+      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      conv3x3_roll_kernel<true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles);
+    } else {
+      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      conv3x3_roll_kernel<false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles);
+    }
+    TATT_LAUNCH_CHECK("conv3x3_roll_kernel");
+    return 0;
   }
   constexpr int A_PLANE = ((((R + 2) * HALO_W) * 128 + 1023) / 1024) * 1024;
   const int smem = 2 * A_PLANE + NSTAGE * B_TAP_BYTES + 1024;
