@@ -273,14 +273,17 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
       : "memory");
 }
 
+constexpr int RL_NSTAGE = 4;                                  // weight-tap ring (4 x 16 KB) + 16 KB of epilogue staging
+constexpr int RL_STG_BYTES = 4 * 32 * 128;                    // per epilogue warp: [32 px][32 ch] fp32
+
 template <bool single>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                    float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles) {
+                    float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles, int dbg) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) unsigned long long pair_full[2], pair_empty[2], w_full[NSTAGE], w_empty[NSTAGE], acc_full[2],
+  __shared__ __align__(8) unsigned long long pair_full[2], pair_empty[2], w_full[RL_NSTAGE], w_empty[RL_NSTAGE], acc_full[2],
       acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -288,6 +291,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   const int t0 = (int)((long long)blockIdx.x * ntiles / gridDim.x);
   const int t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
   const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + RL_A_PLANE, b_ring = a_lo + RL_A_PLANE;
+  unsigned char* stg_base = smem + 2 * RL_A_PLANE + RL_NSTAGE * B_TAP_BYTES;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -296,7 +300,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       mbar_init(smem_u32(&acc_full[i]), 1);
       mbar_init(smem_u32(&acc_empty[i]), 4);
     }
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < RL_NSTAGE; ++s) {
       mbar_init(smem_u32(&w_full[s]), 1);
       mbar_init(smem_u32(&w_empty[s]), 1);
     }
@@ -341,12 +345,13 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           if (pr) ++nload1; else ++nload0;
         }
         for (int tap = 0; tap < 9; ++tap) {
+          if ((dbg & 2) && (t > t0 || tap >= RL_NSTAGE)) break;
           if (wrapped) mbar_wait(smem_u32(&w_empty[ws]), wpar);
           const uint32_t dst = b_ring + (uint32_t)(ws * B_TAP_BYTES);
           mbar_expect_tx(smem_u32(&w_full[ws]), (uint32_t)(single ? B_TAP_BYTES / 2 : B_TAP_BYTES));
           tma_load_2d(dst, &tmBh, smem_u32(&w_full[ws]), tap * 64, 0);
           if (!single) tma_load_2d(dst + 64 * 128, &tmBl, smem_u32(&w_full[ws]), tap * 64, 0);
-          if (++ws == NSTAGE) {
+          if (++ws == RL_NSTAGE) {
             ws = 0;
             if (wrapped) wpar ^= 1;
             wrapped = true;
@@ -391,9 +396,12 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             mbar_wait(smem_u32(&pair_full[p1]), (uint32_t)((p1 ? nfull1 : nfull0) & 1));
             if (p1) ++nfull1; else ++nfull0;
           }
-          mbar_wait(smem_u32(&w_full[ws]), wpar);
+          if (!((dbg & 2) && (t > t0 || tap >= RL_NSTAGE))) mbar_wait(smem_u32(&w_full[ws]), wpar);
           tc_fence_after();
           const uint32_t bh = ((b_ring + (uint32_t)(ws * B_TAP_BYTES)) >> 4) | LBO1, bl = bh + ((64 * 128) >> 4);
+          // per output row: lo*hi, hi*lo, hi*hi back to back (consecutive MMAs that share an operand are cheaper: the
+          // N = 64 MMAs are bound by shared-memory operand fetch, ~80 cycles each instead of the 32-cycle math floor;
+          // alternating the two rows' accumulators was measured 15 % slower)
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
             const uint32_t ah = rowh[r + ky] + (uint32_t)(kx * 8), al = rowl[r + ky] + (uint32_t)(kx * 8);
@@ -410,7 +418,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             }
           }
           umma_commit_elect(smem_u32(&w_empty[ws]));
-          if (++ws == NSTAGE) {
+          if (++ws == RL_NSTAGE) {
             ws = 0;
             wpar ^= 1;
           }
@@ -422,33 +430,45 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
+    // TMEM -> registers -> warp-private swizzled staging -> 128-byte coalesced row segments (a direct store would
+    // scatter 16-byte pieces at a 256-byte stride: 32 sectors per instruction, which throttles the LSU)
     const int lg = warp & 3;
+    unsigned char* stg = stg_base + lg * (32 * 128);
+    const int pq = lane >> 3, cc = lane & 7;          // copy-out: pixel 4 i + pq, float4 column cc of the 32-channel half
+    float4 bb[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      bb[h] = bias ? __ldg(reinterpret_cast<const float4*>(bias + h * 32 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     int it = 0;
     for (int t = t0; t < t1; ++t, ++it) {
       const int yb = t % nyb, xb = (t / nyb) % nxt, n = t / (nyb * nxt);
-      const int y0 = 2 * yb, px = xb * TW + lg * 32 + lane;
+      const int y0 = 2 * yb, px0 = xb * TW + lg * 32;
       mbar_wait(smem_u32(&acc_full[it & 1]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        float* dst = Y + (((long long)n * H + (y0 + r)) * W + px) * 64;
+        float* dst = Y + (((long long)n * H + (y0 + r)) * W + px0 + pq) * 64 + cc * 4;
 #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((it & 1) * 128 + r * 64 + c16 * 16), v);
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 o;
-            o.x = __uint_as_float(v[4 * q + 0]);
-            o.y = __uint_as_float(v[4 * q + 1]);
-            o.z = __uint_as_float(v[4 * q + 2]);
-            o.w = __uint_as_float(v[4 * q + 3]);
-            if (bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c16 * 16 + 4 * q));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            *reinterpret_cast<float4*>(dst + c16 * 16 + 4 * q) = o;
+          for (int c16 = 0; c16 < 2; ++c16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((it & 1) * 128 + r * 64 + h * 32 + c16 * 16), v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(stg + lane * 128 + (((4 * c16 + q) ^ (lane & 7)) << 4)) =
+                  make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                              __uint_as_float(v[4 * q + 3]));
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int p = 4 * i + pq;
+            float4 o = *reinterpret_cast<const float4*>(stg + p * 128 + ((cc ^ (p & 7)) << 4));
+            o.x += bb[h].x; o.y += bb[h].y; o.z += bb[h].z; o.w += bb[h].w;
+            if (!(dbg & 1)) *reinterpret_cast<float4*>(dst + (long long)(4 * i) * 64 + h * 32) = o;
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -682,17 +702,21 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
     }
   }
   if (mode == 3) {
-    const int smem = 2 * RL_A_PLANE + NSTAGE * B_TAP_BYTES + 1024;
+    const int smem = 2 * RL_A_PLANE + RL_NSTAGE * B_TAP_BYTES + RL_STG_BYTES + 1024;
     const int ntiles = nimg * (H / 2) * (W / TW);
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const int grid = ntiles < nsm ? ntiles : nsm;
+    static const int dbg = []() {
+      const char* e = getenv("TATT_ROLL_DBG");
+      return e ? atoi(e) : 0;
+    }();
     if (single) {
       TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles);
+      conv3x3_roll_kernel<true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
     } else {
       TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles);
+      conv3x3_roll_kernel<false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
     }
     TATT_LAUNCH_CHECK("conv3x3_roll_kernel");
     return 0;
