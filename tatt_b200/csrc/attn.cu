@@ -46,7 +46,7 @@ __device__ __forceinline__ void probs(const float qv[HD], const float (*Ks)[DM],
   float sum = 0.f;
 #pragma unroll
   for (int j = 0; j < LKMAX; ++j) {
-    float e = (j < Lk) ? expf(p[j] - mx) : 0.f;
+    float e = (j < Lk) ? __expf(p[j] - mx) : 0.f;   // ex2.approx: ~2 ulp, far inside the 1e-3 tolerance
     p[j] = e;
     sum += e;
   }
@@ -55,17 +55,25 @@ __device__ __forceinline__ void probs(const float qv[HD], const float (*Ks)[DM],
   for (int j = 0; j < LKMAX; ++j) p[j] *= inv;
 }
 
-// keep-mask scale factors (0 or 1/(1-p)) for the 32 key slots of element (n,h,q)
+// keep-mask scale factors (0 or 1/(1-p)) for the 32 key slots of element (n,h,q).  16 random bits per slot (keep iff
+// u16 >= round(p * 65536): the keep probability is exact to 2^-16), i.e. four Philox4x32 calls per (query, head)
+// instead of eight -- the kernels are bound by this integer work, not by the 26 x 16 dot products.
 __device__ __forceinline__ void drop_scales(float ds[LKMAX], float pdrop, unsigned long long seed,
                                             unsigned long long offset, long long elem) {
   const float sc = 1.f / (1.f - pdrop);
+  const uint32_t thr = (uint32_t)(pdrop * 65536.f + 0.5f);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
-  for (int j4 = 0; j4 < LKMAX / 4; ++j4) {
-    float4 u = philox_uniform4(seed, offset, (unsigned long long)(elem * (LKMAX / 4) + j4));
-    ds[j4 * 4 + 0] = u.x >= pdrop ? sc : 0.f;
-    ds[j4 * 4 + 1] = u.y >= pdrop ? sc : 0.f;
-    ds[j4 * 4 + 2] = u.z >= pdrop ? sc : 0.f;
-    ds[j4 * 4 + 3] = u.w >= pdrop ? sc : 0.f;
+  for (int j8 = 0; j8 < LKMAX / 8; ++j8) {
+    const unsigned long long idx = (unsigned long long)(elem * (LKMAX / 8) + j8);
+    const uint4 r = philox4x32_10(key, make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset,
+                                                  (uint32_t)(offset >> 32)));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ds[j8 * 8 + 2 * k + 0] = (w[k] & 0xffffu) >= thr ? sc : 0.f;
+      ds[j8 * 8 + 2 * k + 1] = (w[k] >> 16) >= thr ? sc : 0.f;
+    }
   }
 }
 

@@ -384,7 +384,7 @@ static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0;
 static int run_gemm(GemmP p, int amode, int bmode, bool want_split, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return 0;
   // vector-access eligibility
-  int fl = p.flags & (F_ACCUM | F_RELU | F_APLANES | F_BPLANES | F_BF16);
+  int fl = p.flags & (F_ACCUM | F_RELU | F_APLANES | F_BPLANES | F_BF16 | F_A_VALID);
   bool va, vb;
   if (amode == A_ROW || amode == A_COL)
     va = (p.lda % 4 == 0) && aligned16(p.A) && (p.sA % 4 == 0);
@@ -708,7 +708,7 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv2d_igemm: too many pixels");
   if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout == 64 && ws &&
       !(flags & (F_ACCUM | F_RELU | F_FP32))) {
-    int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, (flags & F_BF16) ? 1 : 0, ws, ws_bytes,
+    int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws, ws_bytes,
                                      (cudaStream_t)stream);
     if (rc >= 0) return rc;
   }
@@ -717,7 +717,7 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
   p.M = nimg * H * W; p.N = Cout; p.K = KH * KW * Cin;
   p.lda = 0; p.ldb = Cout; p.ldc = Cout;
   p.batch = 1;
-  p.flags = flags & (F_ACCUM | F_RELU | F_BF16);
+  p.flags = flags & (F_ACCUM | F_RELU | F_BF16 | F_A_VALID);
   p.no_tc = (flags & F_FP32) ? 1 : 0;
   p.ws = ws;
   p.ws_bytes = ws_bytes;
@@ -734,7 +734,8 @@ int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int
   cudaStream_t st = (cudaStream_t)stream;
   TATT_CUDA(cudaMemsetAsync(dWt, 0, sizeof(float) * (size_t)KH * KW * Cin * Cout, st));
   if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout == 64 && ws && !(flags & F_FP32)) {
-    int rc = tatt_tc3_conv3x3_wgrad_launch(X, dY, dWt, nimg, H, W, (flags & F_BF16) ? 1 : 0, ws, ws_bytes, st);
+    int rc = tatt_tc3_conv3x3_wgrad_launch(X, dY, dWt, nimg, H, W, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
+                                           ws_bytes, st);
     if (rc >= 0) return rc;
   }
   GemmP p = {};
@@ -742,7 +743,7 @@ int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int
   p.M = KH * KW * Cin; p.N = Cout; p.K = nimg * H * W;
   p.lda = 0; p.ldb = Cout; p.ldc = Cout;
   p.batch = 1;
-  p.flags = flags & F_BF16;
+  p.flags = flags & (F_BF16 | F_A_VALID);
   p.no_tc = (flags & F_FP32) ? 1 : 0;
   p.ws = ws;
   p.ws_bytes = ws_bytes;

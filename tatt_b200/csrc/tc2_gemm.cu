@@ -695,7 +695,7 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
       rc = split_dense(Ab, p.lda, p.M, p.K, p.K, Ahi + b * q.sA, Alo + b * q.sA, st);
     else if (kind == K2_DENSE_MN)
       rc = split_dense(Ab, p.lda, p.K, p.M, (int)q.lda, Ahi + b * q.sA, Alo + b * q.sA, st);
-    else if (b == 0)
+    else if (b == 0 && !(p.flags & F_A_VALID))       // F_A_VALID: the workspace still holds these planes
       rc = split_dense(Ab, p.cC, nA / p.cC, p.cC, p.cC, Ahi, Alo, st);
     if (rc) return rc;
     if (b_pl) {

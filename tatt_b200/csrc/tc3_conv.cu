@@ -657,7 +657,7 @@ static inline long long rup8(long long x) { return (x + 7) & ~7LL; }
 
 // conv3x3 64->64 through the TMA kernel.  Returns 0 ok, 1 error, -1 not eligible (caller falls through).
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
-                            int single, void* ws, long long ws_bytes, cudaStream_t st) {
+                            int single, int a_valid, void* ws, long long ws_bytes, cudaStream_t st) {
   static const int mode = []() {          // TATT_TMA: 0 = off, 1 / 2 = one tile per CTA (base_offset 0 / from address),
     const char* e = getenv("TATT_TMA");   //           3 = persistent rolling-halo kernel (default)
     return e ? atoi(e) : 3;
@@ -670,7 +670,7 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
   if ((long long)sizeof(__nv_bfloat16) * 2 * (nA + nB) > ws_bytes || (((uintptr_t)ws) & 15)) return -1;
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16 *Ahi = base, *Alo = base + nA, *Bhi = base + 2 * nA, *Blo = base + 2 * nA + nB;
-  int rc = tatt_tc2_split(X, 64, P, 64, 0, Ahi, Alo, nullptr, st);          // activations -> [P][64] planes
+  int rc = a_valid ? 0 : tatt_tc2_split(X, 64, P, 64, 0, Ahi, Alo, nullptr, st);   // activations -> [P][64] planes
   if (rc) return rc;
   rc = tatt_tc2_split(Wt, 64, 576, 64, 1, Bhi, Blo, nullptr, st);            // Wt[576][64] -> planes [64 co][576 k]
   if (rc) return rc;
@@ -732,7 +732,7 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
 
 // conv3x3 64->64 weight gradient through the TMA kernel; dWt must be zeroed by the caller.  Same return convention.
 int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int single,
-                                  void* ws, long long ws_bytes, cudaStream_t st) {
+                                  int a_valid, void* ws, long long ws_bytes, cudaStream_t st) {
   static const int mode = []() {
     const char* e = getenv("TATT_TMA_WGRAD");
     return e ? atoi(e) : 1;
@@ -746,7 +746,7 @@ int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, i
   if (plane_bytes > ws_bytes || (((uintptr_t)ws) & 15)) return -1;
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16 *Xh = base, *Xl = base + nA, *Gh = base + 2 * nA, *Gl = base + 3 * nA;
-  int rc = tatt_tc2_split(X, 64, P, 64, 0, Xh, Xl, nullptr, st);
+  int rc = a_valid ? 0 : tatt_tc2_split(X, 64, P, 64, 0, Xh, Xl, nullptr, st);
   if (rc) return rc;
   rc = tatt_tc2_split(dY, 64, P, 64, 0, Gh, Gl, nullptr, st);
   if (rc) return rc;

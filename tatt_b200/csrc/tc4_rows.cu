@@ -65,6 +65,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// warp-uniform issue: the whole warp runs the (uniform) surrounding code, one elected lane issues -- keeps descriptors in
+// uniform registers instead of a per-lane waterfall loop around every UTCHMMA
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -350,8 +372,9 @@ struct WgP {
   int flags;
 };
 
+// one slab in flight per CTA (the 2-deep variant below spills at NB = 3 and was measured slower there)
 template <int NB>
-__global__ void __launch_bounds__(NT, (NB == 3) ? 2 : 3) rows_wgrad_kernel(const WgP p) {
+__global__ void __launch_bounds__(NT, (NB == 3) ? 2 : 3) rows_wgrad1_kernel(const WgP p) {
   constexpr uint32_t TCOLS = (NB == 1) ? 64u : ((NB == 2) ? 128u : 256u);
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -503,6 +526,172 @@ __global__ void __launch_bounds__(NT, (NB == 3) ? 2 : 3) rows_wgrad_kernel(const
   }
 }
 
+template <int NB>
+__global__ void __launch_bounds__(NT, 2) rows_wgrad_kernel(const WgP p) {
+  constexpr uint32_t TCOLS = (NB == 1) ? 64u : ((NB == 2) ? 128u : 256u);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[WG_LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool single = (p.flags & F_BF16) != 0;
+  // [A hi][A lo][B hi][B lo], one 64-channel MN block each.  The MMA's M is 128: the second 64-channel block of the A
+  // descriptors (leading-dimension byte offset = PLANE) aliases the NEXT plane -- finite bf16 data whose products land
+  // in accumulator rows 64..127, which are never read.
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = smem + PLANE;
+  unsigned char* b_hi = smem + 2 * PLANE;
+  unsigned char* b_lo = smem + 3 * PLANE;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(TCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < 4 * PLANE / 16; i += NT) *reinterpret_cast<uint4*>(smem + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < WG_LD; i += NT) red[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bar_a = smem_u32(&bar);
+  // M = 128, N = 64, A and B MN-major (bits 15, 16)
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+  float cs[NB][4];
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cs[j][q] = 0.f;
+
+  const int r0 = tid >> 4, c4 = tid & 15;
+  const int st_off = slab_st_off(tid);
+  const int acol = (c4 < 8) ? (p.a_off0 + c4 * 4) : (p.a_off1 + (c4 - 8) * 4);
+  // The slab stream of this CTA (per 128-row block: A, B_0 .. B_{NB-1}) is double-buffered in registers with a prefetch
+  // distance of TWO slabs (64 KB in flight per CTA: with ~2.8 us of loaded HBM latency one slab per CTA caps the kernel
+  // at ~3.4 TB/s).  Blocks are processed in pairs so that the buffer of every stream position is a compile-time choice.
+  Slab buf0, buf1;
+  uint32_t ph = 0;
+  bool pending = false;
+  bool first = true;
+  const int g = gridDim.x;
+  int blkA = blockIdx.x;
+  auto sload = [&](Slab& d, int jj) {          // stream position jj relative to the current pair (may reach into the next)
+    int blk = blkA;
+    if (jj >= 2 * (NB + 1)) {
+      blk += 2 * g;
+      jj -= 2 * (NB + 1);
+    }
+    if (jj > NB) {
+      blk += g;
+      jj -= NB + 1;
+    }
+    const long long row0 = (long long)blk * RB + r0;
+    const int rows_left = (blk < p.nblk) ? (int)min((long long)RB, p.M - row0) : 0;
+    if (jj == 0) {
+      slab_load(d, p.A + row0 * p.lda + acol, 16 * p.lda, rows_left);
+    } else {
+      const float* bs = (jj == 1) ? p.B0 : ((jj == 2) ? p.B1 : p.B2);
+      const long long ls = (jj == 1) ? p.ldb0 : ((jj == 2) ? p.ldb1 : p.ldb2);
+      slab_load(d, bs + row0 * ls + c4 * 4, 16 * ls, rows_left);
+    }
+  };
+  sload(buf0, 0);
+  sload(buf1, 1);
+  while (blkA < p.nblk) {
+#pragma unroll
+    for (int j = 0; j < 2 * (NB + 1); ++j) {
+      const int s = j % (NB + 1);
+      Slab& cur = (j & 1) ? buf1 : buf0;
+      if (pending) {           // the previous MMA group still reads A / B
+        cta_wait(bar_a, ph, warp);
+        ph ^= 1;
+        pending = false;
+      }
+      if (s == 0) {
+        slab_store(cur, a_hi + st_off, a_lo + st_off, single);
+        if (p.colsum_src == 1) slab_colsum(cur, cs[0]);
+      } else {
+        slab_store(cur, b_hi + st_off, b_lo + st_off, single);
+        if (p.colsum_src == 2) slab_colsum(cur, cs[(s > 0) ? (s - 1) : 0]);
+      }
+      fence_proxy_async();
+      __syncthreads();
+      sload(cur, j + 2);       // two positions ahead, into the buffer just drained
+      if (s >= 1) {
+        if (warp == 0) {
+          tc_fence_after();
+          const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+          const uint32_t tm = tmem_base + (uint32_t)((s - 1) * 64);
+#pragma unroll
+          for (int k16 = 0; k16 < 8; ++k16) {
+            const uint32_t ko = k16 * 2048;   // 16 pixel rows = two 8-row groups of 1024 B
+            const uint64_t dah = make_desc(ah + ko, PLANE, 1024), dal = make_desc(al + ko, PLANE, 1024);
+            const uint64_t dbh = make_desc(bh + ko, PLANE, 1024), dbl = make_desc(bl + ko, PLANE, 1024);
+            const uint32_t acc = ((first && j <= NB) && k16 == 0) ? 0u : 1u;
+            if (!single) {
+              umma_bf16_elect(tm, dal, dbh, idesc, acc);
+              umma_bf16_elect(tm, dah, dbl, idesc, 1u);
+              umma_bf16_elect(tm, dah, dbh, idesc, 1u);
+            } else {
+              umma_bf16_elect(tm, dah, dbh, idesc, acc);
+            }
+          }
+          umma_commit_elect(bar_a);
+        }
+        pending = true;
+      }
+    }
+    first = false;
+    blkA += 2 * g;
+  }
+  if (pending) {
+    cta_wait(bar_a, ph, warp);
+    ph ^= 1;
+  }
+  tc_fence_after();
+  float* part = p.partial + (long long)blockIdx.x * WG_PART;
+  const int lg = warp & 3, half = warp >> 2;
+  if (lg < 2) {                      // accumulator rows 64..127 are padding
+    const int row = lg * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+      for (int c16 = 0; c16 < 2; ++c16) {
+        uint32_t v[16];
+        const int col0 = j * 64 + half * 32 + c16 * 16;
+        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)col0, v);
+        float4* dst = reinterpret_cast<float4*>(part + row * WG_LD + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                               __uint_as_float(v[4 * q + 3]));
+      }
+    }
+  }
+  if (p.colsum_src) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (j == 0 || p.colsum_src == 2) atomicAdd(&red[j * 64 + c4 * 4 + q], cs[j][q]);
+    __syncthreads();
+    for (int i = tid; i < WG_LD; i += NT) part[64 * WG_LD + i] = red[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
+  }
+}
+
 // D[r][c] = sum over the per-CTA partial tiles (coalesced reads, 4 part groups per element, fixed summation order),
 // then scattered to out[b][i][j] with D[b rb + (T ? j : i)][b cb + (T ? i : j)];  rows >= 64 of the index space are the
 // column sums -> dbias
@@ -553,6 +742,12 @@ static int launch_rows_gemm(const RowsP& p, cudaStream_t st) {
 template <int NB>
 static int launch_rows_wgrad(const WgP& p, int grid, cudaStream_t st) {
   const int smem = 4 * PLANE + 1024;
+  if (NB == 3) {
+    TATT_CUDA(cudaFuncSetAttribute(rows_wgrad1_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rows_wgrad1_kernel<NB><<<grid, NT, smem, st>>>(p);
+    TATT_LAUNCH_CHECK("rows_wgrad1_kernel");
+    return 0;
+  }
   TATT_CUDA(cudaFuncSetAttribute(rows_wgrad_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   rows_wgrad_kernel<NB><<<grid, NT, smem, st>>>(p);
   TATT_LAUNCH_CHECK("rows_wgrad_kernel");
@@ -616,7 +811,7 @@ int tatt_rows_wgrad(const float* A, long long lda, int a_off0, int a_off1, const
   p.M = M;
   p.nblk = (int)((M + RB - 1) / RB);
   p.colsum_src = colsum_src; p.flags = flags;
-  int grid = ((NB == 3) ? 2 : 3) * num_sms();
+  int grid = 2 * num_sms();
   if (grid > WG_MAX_GRID) grid = WG_MAX_GRID;
   if (grid > p.nblk) grid = p.nblk;
   TATT_REQUIRE((long long)grid * WG_PART * (long long)sizeof(float) <= ws_bytes,

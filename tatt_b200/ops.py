@@ -12,7 +12,7 @@ from . import _cabi
 
 Tensor = torch.Tensor
 ACT_NONE, ACT_RELU, ACT_MISH = 0, 1, 2
-F_ACCUM, F_RELU, F_SPLITK, F_ZEROC, F_FP32, F_APLANES, F_BPLANES, F_BF16 = 1, 2, 4, 64, 128, 256, 512, 1024
+F_ACCUM, F_RELU, F_SPLITK, F_ZEROC, F_FP32, F_APLANES, F_BPLANES, F_BF16, F_A_VALID = 1, 2, 4, 64, 128, 256, 512, 1024, 2048
 _precision_flag = 0      # OR-ed into every GEMM / conv call; F_FP32 inside `full_fp32()`
 
 
@@ -314,8 +314,20 @@ def conv_pack(w: Tensor, cin_p: int, cout_p: int, flip: bool) -> Tensor:
     return wt
 
 
-def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int) -> Tensor:
-    """x [N,H,W,CinP] (CinP >= w.shape[1], multiple of 4) -> y [N,H,W,CoutP]"""
+def _conv_ws(x: Tensor, nx: int, ndy: int, extra: int):
+    """One scratch buffer per convolution layer, laid out so that the bf16 hi/lo planes written by one pass are
+    reused by the next (F_A_VALID): [X planes: 2 x nx bf16][dY planes: 2 x ndy bf16][weights planes / split-K tiles].
+    forward: workspace base = 0 (A = X); weight gradient: base = 0 (A = X valid, B = dY split here);
+    data gradient: base = the dY planes (A = dY valid)."""
+    if _precision_flag & F_FP32:
+        return None
+    nbytes = 4 * (_r8(nx) + _r8(ndy) + extra) + 1024
+    return torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+
+
+def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Optional[dict] = None) -> Tensor:
+    """x [N,H,W,CinP] (CinP >= w.shape[1], multiple of 4) -> y [N,H,W,CoutP].  `keep` (a dict owned by the caller's
+    tape entry) receives the workspace whose X planes the backward pass reuses."""
     n, h, wd, cin_p = x.shape
     co, ci, kh, kw = w.shape
     cout_p = _pad4(co)
@@ -324,46 +336,65 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int) -> Tensor:
         bp[:co].copy_(b)
         b = bp
     y = empty(n, h, wd, cout_p, like=x)
+    P = n * h * wd
     if cout_p == 4 and kw > 1 and cin_p >= 16:
         # kx-expansion (see gemm.cu): vertical-tap GEMM with N = kw*4, then a horizontal shift-sum
         wte = empty(kh * cin_p, kw * 4, like=x)
         _cabi.call("tatt_conv_kxexp_pack", _p(w.contiguous()), _p(wte), co, ci, kh, kw, cin_p, 4, _stream())
-        t = empty(n * h * wd, kw * 4, like=x)
-        ws, wsb = _ws(x, x.numel() + kh * cin_p * _r8(kw * 4))
+        t = empty(P, kw * 4, like=x)
+        ws = _conv_ws(x, x.numel(), P * _r8(kw * 4), kh * cin_p * _r8(kw * 4) + 148 * kh * cin_p * _r8(kw * 4))
         _cabi.call("tatt_conv2d_igemm", _p(x), _p(wte), None, _p(t), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0,
-                   _precision_flag, _p(ws), wsb, _stream())
-        _cabi.call("tatt_conv_kxexp_reduce", _p(t), _p(b), _p(y), n * h * wd, wd, kw, 4, pad, _stream())
+                   _precision_flag, _p(ws), 0 if ws is None else ws.numel(), _stream())
+        _cabi.call("tatt_conv_kxexp_reduce", _p(t), _p(b), _p(y), P, wd, kw, 4, pad, _stream())
+        if keep is not None:
+            keep["ws"] = ws
         return y
     wt = conv_pack(w, cin_p, cout_p, False)
-    ws, wsb = _ws(x, x.numel() + kh * kw * cin_p * _r8(cout_p))
+    ws = _conv_ws(x, x.numel(), P * _r8(cout_p),
+                  max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
     _cabi.call("tatt_conv2d_igemm", _p(x), _p(wt), _p(b), _p(y), n, h, wd, cin_p, cout_p, kh, kw, pad, pad,
-               _precision_flag, _p(ws), wsb, _stream())
+               _precision_flag, _p(ws), 0 if ws is None else ws.numel(), _stream())
+    if keep is not None:
+        keep["ws"] = ws
     return y
 
 
 def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True, need_dw: bool = True,
-               has_bias: bool = True):
+               has_bias: bool = True, keep: Optional[dict] = None):
     """-> (dx [N,H,W,CinP] | None, dW [Cout,Cin,KH,KW] | None, db [Cout] | None)"""
     n, h, wd, cin_p = x.shape
     co, ci, kh, kw = w.shape
     cout_p = dy.shape[-1]
+    P = n * h * wd
     dx = dw = db = None
-    if need_dw and cout_p == 4 and kw > 1 and cin_p >= 16:
-        dt = empty(n * h * wd, kw * 4, like=x)
-        _cabi.call("tatt_conv_kxexp_expand", _p(dy), _p(dt), n * h * wd, wd, kw, 4, pad, _stream())
+    kx = cout_p == 4 and kw > 1 and cin_p >= 16
+    ndy = P * _r8(kw * 4) if kx else P * _r8(cout_p)
+    extra = (kh * cin_p * _r8(kw * 4) + 148 * kh * cin_p * _r8(kw * 4)) if kx else (
+        max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
+    ws = keep.get("ws") if keep is not None else None
+    # X planes written by the forward pass (only the shapes whose forward AND weight-gradient run on the plane engines)
+    x_valid = ws is not None and not (_precision_flag & F_FP32) and cin_p % 64 == 0 and P >= 128
+    if ws is None:
+        ws = _conv_ws(x, x.numel(), ndy, extra)
+    wsb = 0 if ws is None else ws.numel()
+    dy_valid = False
+    if need_dw and kx:
+        dt = empty(P, kw * 4, like=x)
+        _cabi.call("tatt_conv_kxexp_expand", _p(dy), _p(dt), P, wd, kw, 4, pad, _stream())
         dwte = empty(kh * cin_p, kw * 4, like=x)
-        ws, wsb = _ws(x, x.numel() + n * h * wd * _r8(kw * 4))
-        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dt), _p(dwte), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0, _precision_flag,
-                   _p(ws), wsb, _stream())
+        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dt), _p(dwte), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0,
+                   _precision_flag | (F_A_VALID if x_valid else 0), _p(ws), wsb, _stream())
         dw = empty(co, ci, kh, kw, like=x)
         _cabi.call("tatt_conv_kxexp_unpack_grad", _p(dwte), _p(dw), co, ci, kh, kw, cin_p, 4, _stream())
         if has_bias:
             db = colsum(dy.view(-1, cout_p))[:co]
     elif need_dw:
         dwt = empty(kh * kw * cin_p, cout_p, like=x)
-        ws, wsb = _ws(x, x.numel() + n * h * wd * _r8(cout_p) + 148 * kh * kw * cin_p * cout_p + 16)
-        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dy), _p(dwt), n, h, wd, cin_p, cout_p, kh, kw, pad, pad, _precision_flag,
-                   _p(ws), wsb, _stream())
+        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dy), _p(dwt), n, h, wd, cin_p, cout_p, kh, kw, pad, pad,
+                   _precision_flag | (F_A_VALID if x_valid else 0), _p(ws), wsb, _stream())
+        # the tcgen05 weight-gradient kernels leave the dY planes right behind the X planes
+        dy_valid = (ws is not None and _conv_share_dy and kh == 3 and kw == 3 and cin_p == 64 and cout_p in (64, 256)
+                    and P >= 128)
         dw = empty(co, ci, kh, kw, like=x)
         _cabi.call("tatt_conv_weight_unpack_grad", _p(dwt), _p(dw), co, ci, kh, kw, cin_p, cout_p, _stream())
         if has_bias:
@@ -371,10 +402,15 @@ def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True,
     if need_dx:
         wb = conv_pack(w, cin_p, cout_p, True)
         dx = empty(n, h, wd, cin_p, like=x)
-        ws, wsb = _ws(x, dy.numel() + kh * kw * cout_p * _r8(cin_p))
+        off = 4 * _r8(x.numel()) if dy_valid else 0            # bytes: skip the X planes
+        wsd = ws[off:] if ws is not None else None
         _cabi.call("tatt_conv2d_igemm", _p(dy), _p(wb), None, _p(dx), n, h, wd, cout_p, cin_p, kh, kw,
-                   kh - 1 - pad, kw - 1 - pad, _precision_flag, _p(ws), wsb, _stream())
+                   kh - 1 - pad, kw - 1 - pad, _precision_flag | (F_A_VALID if dy_valid else 0), _p(wsd),
+                   0 if wsd is None else wsd.numel(), _stream())
     return dx, dw, db
+
+
+_conv_share_dy = os.environ.get("TATT_CONV_SHARE", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------ norms

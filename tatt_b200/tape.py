@@ -135,13 +135,14 @@ class Tape:
         return y
 
     def conv(self, x4: Tensor, w: Tensor, b: Optional[Tensor], pad: int, need_dx: bool = True) -> Tensor:
-        y = ops.conv2d_fwd(x4, w, b, pad)
+        keep = {} if self.record else None       # workspace whose X planes the backward pass reuses
+        y = ops.conv2d_fwd(x4, w, b, pad, keep=keep)
 
         def bwd():
             dy = self.grad(y)
             if dy is None:
                 return
-            dx, dw, db = ops.conv2d_bwd(x4, w, dy, pad, need_dx=need_dx, has_bias=b is not None)
+            dx, dw, db = ops.conv2d_bwd(x4, w, dy, pad, need_dx=need_dx, has_bias=b is not None, keep=keep)
             self.add_grad(w, dw)
             if b is not None:
                 self.add_grad(b, db)
