@@ -73,6 +73,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// warp-uniform issue: warp 0 runs the (uniform) issue code, one elected lane executes the tcgen05 instruction -- keeps
+// descriptors in uniform registers instead of a per-lane waterfall loop around every UTCHMMA
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -267,7 +289,7 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
       cp_async_wait<0>();
       fence_proxy_async();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
         const uint32_t st = smem_base;
         const uint32_t a_hi = st, a_lo = st + A_PLANE, b_hi = st + 2 * A_PLANE, b_lo = b_hi + B_PLANE;
@@ -288,14 +310,14 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
             dbl = make_desc(b_lo + ko, 8192, 1024);
           }
           if (!single) {
-            umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
-            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+            umma_bf16_elect(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+            umma_bf16_elect(tmem_base, dah, dbl, idesc, 1u);
+            umma_bf16_elect(tmem_base, dah, dbh, idesc, 1u);
           } else {
-            umma_bf16(tmem_base, dah, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+            umma_bf16_elect(tmem_base, dah, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
           }
         }
-        umma_commit(smem_u32(&mma_done[0]));
+        umma_commit_elect(smem_u32(&mma_done[0]));
       }
     }
   } else {
@@ -309,7 +331,7 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
       cp_async_wait<STAGES - 2>();
       fence_proxy_async();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
         const uint32_t st = smem_base + (uint32_t)(s * STAGE_BYTES);
         const uint32_t a_hi = st, a_lo = st + A_PLANE, b_hi = st + 2 * A_PLANE, b_lo = b_hi + B_PLANE;
@@ -330,14 +352,14 @@ __global__ void __launch_bounds__(NT, (STAGES == 1) ? 4 : ((STAGES == 2) ? 2 : 1
             dbl = make_desc(b_lo + ko, 8192, 1024);
           }
           if (!single) {
-            umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
-            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+            umma_bf16_elect(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+            umma_bf16_elect(tmem_base, dah, dbl, idesc, 1u);
+            umma_bf16_elect(tmem_base, dah, dbh, idesc, 1u);
           } else {
-            umma_bf16(tmem_base, dah, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+            umma_bf16_elect(tmem_base, dah, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
           }
         }
-        umma_commit(smem_u32(&mma_done[s]));
+        umma_commit_elect(smem_u32(&mma_done[s]));
       }
       // refill the stage consumed at iteration kt-1 (its MMAs were committed to mma_done[(kt-1)%STAGES])
       const int nxt = kt + STAGES - 1;

@@ -263,6 +263,17 @@ __device__ __forceinline__ void umma_lo_elect(uint32_t tmem_c, uint32_t a_lo32, 
       "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(acc), "r"(HI)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t"
@@ -558,7 +569,7 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                             // whole warp, uniform control flow; one elected lane issues
       // M = 128, N = 64, A and B MN-major (bits 15, 16)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -581,17 +592,17 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
             const uint64_t dbh = make_desc_mn(g_hi + ko, 8192), dbl = make_desc_mn(g_lo + ko, 8192);
             const uint32_t tm = tmem_base + (uint32_t)(mt * 64);
             if (!single) {
-              umma_bf16(tm, dal, dbh, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
-              umma_bf16(tm, dah, dbl, idesc, 1u);
-              umma_bf16(tm, dah, dbh, idesc, 1u);
+              umma_bf16_elect(tm, dal, dbh, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+              umma_bf16_elect(tm, dah, dbl, idesc, 1u);
+              umma_bf16_elect(tm, dah, dbh, idesc, 1u);
             } else {
-              umma_bf16(tm, dah, dbh, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+              umma_bf16_elect(tm, dah, dbh, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
             }
           }
         }
-        umma_commit(smem_u32(&bar_empty[s]));
+        umma_commit_elect(smem_u32(&bar_empty[s]));
       }
-      umma_commit(smem_u32(&bar_done));
+      umma_commit_elect(smem_u32(&bar_done));
     }
   } else if (nt > 0) {
     mbar_wait(smem_u32(&bar_done), 0);

@@ -57,6 +57,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t da, uint64_t
       "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
+// warp-uniform issue (see tc2_gemm.cu): warp 0 runs the issue code, one elected lane executes the tcgen05 instruction
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -365,7 +386,7 @@ __global__ void __launch_bounds__(NT, (BN == 64) ? 2 : 1) tc_gemm_kernel(const G
     if (kt + 1 < nk) load_regs(kbeg + (kt + 1) * BK);
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
       const uint32_t a_lo = a_hi + A_PLANE;
@@ -377,14 +398,14 @@ __global__ void __launch_bounds__(NT, (BN == 64) ? 2 : 1) tc_gemm_kernel(const G
         const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
         const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
         if (!(p.flags & F_BF16)) {
-          umma_bf16(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);   // small terms first
-          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+          umma_bf16_elect(tmem_base, dal, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);   // small terms first
+          umma_bf16_elect(tmem_base, dah, dbl, idesc, 1u);
+          umma_bf16_elect(tmem_base, dah, dbh, idesc, 1u);
         } else {
-          umma_bf16(tmem_base, dah, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);   // bf16 mode
+          umma_bf16_elect(tmem_base, dah, dbh, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);   // bf16 mode
         }
       }
-      umma_commit(smem_u32(&mma_done[s]));
+      umma_commit_elect(smem_u32(&mma_done[s]));
     }
   }
 
