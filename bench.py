@@ -27,7 +27,7 @@ import torch  # noqa: E402
 
 METRIC = "SR images/sec (32x128 LR, fwd+bwd)"
 UNIT = "images/s"
-NCU_CONV_TRAFFIC_BYTES = 178.2e6         # split pass 91.1 MB + conv3x3_tma_kernel 87.1 MB (profiles/r1_ncu_full_tc*_conv3x3*.csv)
+NCU_CONV_TRAFFIC_BYTES = 182.5e6         # split pass 91.1 MB + conv3x3_roll_kernel 91.4 MB (profiles/r1d_ncu_full_conv3x3_roll.csv)
 ALG_FLOPS_FWD_BWD_G32 = 3.0 * 9.33e9     # ~9.33 GFLOP/img forward (RPE input-proj hoisted) x3 for fwd+bwd
 
 
@@ -130,10 +130,12 @@ def run_reference(args):
 
 
 def conv_roofline(dev, batch, h, w, peaks):
-    """Dominant kernel = the 3x3 64->64 implicit-GEMM convolution on tcgen05 (11 forward instances per image plus
-    their data/weight gradients).  One "launch" = the operand split pass + tc2_gemm_kernel<IM2COL_K> of one conv.
-    Algorithmic FLOPs per launch = 2 * pixels * 64 * 576 (SURVEY 8d conv figure x pixels); timed alone with CUDA
-    events on the launching stream, L2 flushed (256 MB write) between launches."""
+    """Dominant kernel family = the 3x3 64->64 implicit-GEMM convolution on tcgen05 (11 forward instances per image
+    plus their data / weight gradients).  One "launch" = the operand split pass + conv3x3_roll_kernel of one conv, as
+    the model's forward issues it.  Algorithmic FLOPs per launch = 2 * pixels * 64 * 576 (SURVEY 8d conv figure x
+    pixels); timed alone with CUDA events on the launching stream, L2 flushed (256 MB write) between launches.
+    `kernel_only_*`: the same call with the bf16 planes already in the workspace (flag 2048: what the data-gradient
+    pass does), i.e. conv3x3_roll_kernel by itself."""
     from tatt_b200 import _cabi, ops
     x = torch.randn(batch, h, w, 64, device=dev)
     wt = torch.randn(64, 64, 3, 3, device=dev) * 0.05
@@ -142,31 +144,40 @@ def conv_roofline(dev, batch, h, w, peaks):
     ws, wsb = ops._ws(x, x.numel() + 576 * 64)
     for _ in range(3):
         ops.conv2d_fwd(x, wt, b, 1)
-    ts = []
-    for _ in range(10):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        wtp = ops.conv_pack(wt, 64, 64, False)
-        y = torch.empty_like(x)
-        e0.record()
-        _cabi.call("tatt_conv2d_igemm", x.data_ptr(), wtp.data_ptr(), b.data_ptr(), y.data_ptr(), batch, h, w, 64, 64,
-                   3, 3, 1, 1, ops._precision_flag, ws.data_ptr(), wsb, ops._stream())
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e-3)
-    t = sum(ts) / len(ts)
+    wtp = ops.conv_pack(wt, 64, 64, False)
+    y = torch.empty_like(x)
+
+    def timed(flags):
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _cabi.call("tatt_conv2d_igemm", x.data_ptr(), wtp.data_ptr(), b.data_ptr(), y.data_ptr(), batch, h, w, 64,
+                       64, 3, 3, 1, 1, ops._precision_flag | flags, ws.data_ptr(), wsb, ops._stream())
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return sum(ts) / len(ts)
+
+    t = timed(0)
+    tk = timed(ops.F_A_VALID)
     flops = 2.0 * batch * h * w * 64 * 576
     peak = peaks.get("bf16_tflops", 1590.0)
-    # dram__bytes_read.sum + dram__bytes_write.sum of split + GEMM kernels from the committed ncu --set full capture
-    # (profiles/r1_ncu_full_tc2_conv3x3.csv), same shape; algorithmic bytes = 67 MB in + 67 MB out
+    # dram__bytes_read.sum + dram__bytes_write.sum of the split pass + conv kernel from the committed ncu --set full
+    # capture (profiles/), same shape; algorithmic bytes = 67 MB in + 67 MB out
     traffic = NCU_CONV_TRAFFIC_BYTES if (batch, h, w) == (64, 32, 128) else None
-    return {"bound": "tensor", "kernel": "split_dense_kernel + conv3x3_tma_kernel<2> (conv3x3 64->64, NHWC; TMA halo tile "
-            "+ TMA weight ring, tcgen05 kind::f16 with a bf16 hi/lo operand split, 3 MMAs per k-step, fp32 TMEM accumulators)",
+    bf16 = bool(ops._precision_flag & ops.F_BF16)
+    return {"bound": "tensor", "kernel": "split_dense_kernel + conv3x3_roll_kernel (conv3x3 64->64, NHWC; persistent "
+            "rolling-halo TMA tiles + TMA weight ring, tcgen05 kind::f16 with a bf16 hi/lo operand split, 3 MMAs per "
+            "k-step, ping-pong fp32 TMEM accumulators)",
             "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak,
             "traffic": traffic, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if "bf16_tflops" in peaks
             else "fallback 1.59 PFLOP/s, of fallback", "launch_ms": t * 1e3, "algorithmic_flops_per_launch": flops,
-            "note": "fp32-parity mode costs 3 bf16 MMAs per product, so the ceiling of this kernel is 1/3 of the bf16 peak"
-            if not (ops._precision_flag & ops.F_BF16) else "bf16 mode: one MMA per product"}
+            "kernel_only_ms": tk * 1e3, "kernel_only_tflops": flops / tk / 1e12, "kernel_only_frac": flops / tk / 1e12 / peak,
+            "note": ("bf16 mode: one MMA per product" if bf16 else
+                     "fp32-parity mode costs 3 bf16 MMAs per product (ceiling = 1/3 of the bf16 peak); at N = 64 the "
+                     "MMAs are bound by shared-memory operand fetch (~80 cycles each vs the 32-cycle math floor)")}
 
 
 def run_ours(args):

@@ -35,6 +35,80 @@ __global__ void bn_stats_kernel(const float* __restrict__ X, long long P, int C,
   }
 }
 
+// C == 64 fast paths (every BatchNorm2d of the trunk, tsrn.py:878,886,612): float4 loads (16 threads per 256-byte row,
+// 16 rows per pass, 4 passes in flight) instead of one scalar per thread -- the scalar kernels reach ~2 TB/s, these are
+// bound by HBM.  Same accumulation scheme: fp32 partials per thread / CTA, fp64 atomics across CTAs.
+__global__ void __launch_bounds__(256) bn_stats64_kernel(const float4* __restrict__ X, long long P, int rows_per_cta,
+                                                        double* __restrict__ acc) {
+  __shared__ float red[2][16][64];
+  const int c4 = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > P) r1 = P;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+#pragma unroll 4
+  for (long long r = r0 + ty; r < r1; r += 16) {
+    const float4 v = __ldg(X + r * 16 + c4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+  }
+  *reinterpret_cast<float4*>(&red[0][ty][c4 * 4]) = s;
+  *reinterpret_cast<float4*>(&red[1][ty][c4 * 4]) = q;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t += red[which][k][c];
+    atomicAdd(acc + which * 64 + c, (double)t);
+  }
+}
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce64_kernel(const float4* __restrict__ X, const float4* __restrict__ dY, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       int act, long long P, int rows_per_cta, double* __restrict__ acc) {
+  __shared__ float red[2][16][64];
+  const int c4 = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > P) r1 = P;
+  const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + c4), is = __ldg(reinterpret_cast<const float4*>(invstd) + c4);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+#pragma unroll 4
+  for (long long r = r0 + ty; r < r1; r += 16) {
+    const float4 x = __ldg(X + r * 16 + c4);
+    float4 dz = __ldg(dY + r * 16 + c4);
+    const float4 xh = make_float4((x.x - m.x) * is.x, (x.y - m.y) * is.y, (x.z - m.z) * is.z, (x.w - m.w) * is.w);
+    if (act != ACT_NONE) {
+      dz.x *= act_grad(xh.x * g.x + b.x, act);
+      dz.y *= act_grad(xh.y * g.y + b.y, act);
+      dz.z *= act_grad(xh.z * g.z + b.z, act);
+      dz.w *= act_grad(xh.w * g.w + b.w, act);
+    }
+    s.x += dz.x; s.y += dz.y; s.z += dz.z; s.w += dz.w;
+    q.x = fmaf(dz.x, xh.x, q.x); q.y = fmaf(dz.y, xh.y, q.y); q.z = fmaf(dz.z, xh.z, q.z); q.w = fmaf(dz.w, xh.w, q.w);
+  }
+  *reinterpret_cast<float4*>(&red[0][ty][c4 * 4]) = s;
+  *reinterpret_cast<float4*>(&red[1][ty][c4 * 4]) = q;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t += red[which][k][c];
+    atomicAdd(acc + which * 64 + c, (double)t);
+  }
+}
+static inline bool bn64_ok(const void* a, const void* b, int C, long long P) {
+  return C == 64 && P >= 4096 && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+}
+static inline int bn64_rows(long long P) {
+  long long rows = (P + 148 * 8 - 1) / (148 * 8);
+  if (rows < 64) rows = 64;
+  return (int)rows;
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ acc, long long P, int C, float eps, float momentum,
                                    float* __restrict__ mean, float* __restrict__ invstd,
                                    float* __restrict__ running_mean, float* __restrict__ running_var) {
@@ -245,11 +319,17 @@ int tatt_bn_stats(const float* X, long long P, int C, float eps, float momentum,
   cudaStream_t st = (cudaStream_t)stream;
   TATT_REQUIRE(P >= 1 && C >= 1, "bn_stats: empty input");
   TATT_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
-  int rows = 128;
-  if (P > 128LL * 4096) rows = (int)((P + 4095) / 4096);
-  dim3 grid(ceil_div(P, rows), ceil_div(C, 64));
-  bn_stats_kernel<<<grid, 256, 0, st>>>(X, P, C, rows, (double*)ws);
-  TATT_LAUNCH_CHECK("bn_stats_kernel");
+  if (bn64_ok(X, nullptr, C, P)) {
+    const int rows = bn64_rows(P);
+    bn_stats64_kernel<<<ceil_div(P, rows), 256, 0, st>>>(reinterpret_cast<const float4*>(X), P, rows, (double*)ws);
+    TATT_LAUNCH_CHECK("bn_stats64_kernel");
+  } else {
+    int rows = 128;
+    if (P > 128LL * 4096) rows = (int)((P + 4095) / 4096);
+    dim3 grid(ceil_div(P, rows), ceil_div(C, 64));
+    bn_stats_kernel<<<grid, 256, 0, st>>>(X, P, C, rows, (double*)ws);
+    TATT_LAUNCH_CHECK("bn_stats_kernel");
+  }
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)ws, P, C, eps, momentum, mean, invstd,
                                                        running_mean, running_var);
   TATT_LAUNCH_CHECK("bn_finalize_kernel");
@@ -282,11 +362,19 @@ int tatt_bn_bwd(const float* X, const float* dY, const float* mean, const float*
   cudaStream_t st = (cudaStream_t)stream;
   TATT_REQUIRE(P >= 1 && C >= 1, "bn_bwd: empty input");
   TATT_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
-  int rows = 128;
-  if (P > 128LL * 4096) rows = (int)((P + 4095) / 4096);
-  dim3 grid(ceil_div(P, rows), ceil_div(C, 64));
-  bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(X, dY, mean, invstd, gamma, beta, act, P, C, rows, (double*)ws);
-  TATT_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  if (bn64_ok(X, dY, C, P) && bn64_ok(mean, invstd, C, P) && bn64_ok(gamma, beta, C, P)) {
+    const int rows = bn64_rows(P);
+    bn_bwd_reduce64_kernel<<<ceil_div(P, rows), 256, 0, st>>>(reinterpret_cast<const float4*>(X),
+                                                              reinterpret_cast<const float4*>(dY), mean, invstd, gamma,
+                                                              beta, act, P, rows, (double*)ws);
+    TATT_LAUNCH_CHECK("bn_bwd_reduce64_kernel");
+  } else {
+    int rows = 128;
+    if (P > 128LL * 4096) rows = (int)((P + 4095) / 4096);
+    dim3 grid(ceil_div(P, rows), ceil_div(C, 64));
+    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(X, dY, mean, invstd, gamma, beta, act, P, C, rows, (double*)ws);
+    TATT_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  }
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)ws, C, dgamma, dbeta);
   TATT_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   if (dX) {
