@@ -275,39 +275,61 @@ __global__ void rpe_scatter_kernel(const float* __restrict__ dX, float* __restri
 //  GH   [2][Wd][3Hd]  = h_prev W_hh^T + b_hh   (this step)
 //  HALL [2][N+1][Wd][Hd]  hidden states, HALL[:,0] == 0
 //  GATES[N][2][Wd][4][Hd]  r,z,n,ghn (saved)       QPOS [N][Himg*Wd][C]
+// Both gate kernels handle FOUR consecutive hidden units per thread (float4 loads / stores, 8-byte bf16 plane stores):
+// one recurrence step is only 2*Wd*Hd = 262k elements, so the kernel is pure latency -- fewer, fatter threads with
+// independent vector loads cut it roughly in half.  Hd % 4 == 0 and C % 4 == 0 (checked by the launchers).
+__device__ __forceinline__ void split4_store(const float (&x)[4], __nv_bfloat16* hi, __nv_bfloat16* lo, long long i) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
+  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(x[0] - f0.x, x[1] - f0.y), l1 = __floats2bfloat162_rn(x[2] - f1.x, x[3] - f1.y);
+  *reinterpret_cast<uint2*>(hi + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  *reinterpret_cast<uint2*>(lo + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 __global__ void rpe_gate_fwd_kernel(const float* __restrict__ GI, const float* __restrict__ GH,
                                     float* __restrict__ HALL, float* __restrict__ GATES,
                                     float* __restrict__ QPOS, __nv_bfloat16* __restrict__ HPL, long long plane_lo,
                                     int step, int N, int Wd, int Hd, int C, int Himg) {
-  long long n = 2LL * Wd * Hd;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    int j = (int)(i % Hd);
-    long long r = i / Hd;
-    int w = (int)(r % Wd);
-    int dir = (int)(r / Wd);
-    long long g3 = ((long long)dir * Wd + w) * 3 * Hd + j;
-    float gr = GI[g3] + GH[g3];
-    float gz = GI[g3 + Hd] + GH[g3 + Hd];
-    float ghn = GH[g3 + 2 * Hd];
-    float rr = sigmoid_f(gr), zz = sigmoid_f(gz);
-    float nn = tanhf(GI[g3 + 2 * Hd] + rr * ghn);
-    long long hidx = (((long long)dir * (N + 1) + step) * Wd + w) * Hd + j;
-    float hp = HALL[hidx];
-    float hn = nn + zz * (hp - nn);
-    HALL[hidx + (long long)Wd * Hd] = hn;
-    if (HPL) split_bf16(hn, HPL, HPL + plane_lo, hidx + (long long)Wd * Hd);
-    if (GATES) {
-      long long gi = ((((long long)step * 2 + dir) * Wd + w) * 4) * Hd + j;
-      GATES[gi] = rr;
-      GATES[gi + Hd] = zz;
-      GATES[gi + 2 * Hd] = nn;
-      GATES[gi + 3 * Hd] = ghn;
+  const int Hd4 = Hd >> 2;
+  const int n4 = 2 * Wd * Hd4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int j = (i % Hd4) << 2;
+    const int r = i / Hd4;
+    const int w = r % Wd, dir = r / Wd;
+    const long long g3 = ((long long)dir * Wd + w) * 3 * Hd + j;
+    const long long hidx = (((long long)dir * (N + 1) + step) * Wd + w) * Hd + j;
+    float gir[4], giz[4], gin[4], ghr[4], ghz[4], ghn[4], hp[4];
+    ld4(GI + g3, gir); ld4(GI + g3 + Hd, giz); ld4(GI + g3 + 2 * Hd, gin);
+    ld4(GH + g3, ghr); ld4(GH + g3 + Hd, ghz); ld4(GH + g3 + 2 * Hd, ghn);
+    ld4(HALL + hidx, hp);
+    float rr[4], zz[4], nn[4], hn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      rr[k] = sigmoid_f(gir[k] + ghr[k]);
+      zz[k] = sigmoid_f(giz[k] + ghz[k]);
+      nn[k] = tanhf(gin[k] + rr[k] * ghn[k]);
+      hn[k] = nn[k] + zz[k] * (hp[k] - nn[k]);
     }
-    int b = dir == 0 ? step : N - 1 - step;
-    int f = dir * Hd + j;
-    int hh = f / C, c = f % C;
-    QPOS[((long long)b * Himg * Wd + (long long)hh * Wd + w) * C + c] = hn;
+    st4(HALL + hidx + (long long)Wd * Hd, hn);
+    if (HPL) split4_store(hn, HPL, HPL + plane_lo, hidx + (long long)Wd * Hd);
+    if (GATES) {
+      const long long gi = ((((long long)step * 2 + dir) * Wd + w) * 4) * Hd + j;
+      st4(GATES + gi, rr);
+      st4(GATES + gi + Hd, zz);
+      st4(GATES + gi + 2 * Hd, nn);
+      st4(GATES + gi + 3 * Hd, ghn);
+    }
+    const int b = dir == 0 ? step : N - 1 - step;
+    const int f = dir * Hd + j;
+    const int hh = f / C, c = f % C;
+    st4(QPOS + ((long long)b * Himg * Wd + (long long)hh * Wd + w) * C + c, hn);
   }
 }
 
@@ -320,39 +342,46 @@ __global__ void rpe_gate_bwd_kernel(const float* __restrict__ dQPOS, const float
                                     float* __restrict__ DGISUM, float* __restrict__ DGH,
                                     __nv_bfloat16* __restrict__ DGHPL, long long plane_lo, int step, int N, int Wd,
                                     int Hd, int C, int Himg) {
-  long long n = 2LL * Wd * Hd;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    int j = (int)(i % Hd);
-    long long r = i / Hd;
-    int w = (int)(r % Wd);
-    int dir = (int)(r / Wd);
-    int b = dir == 0 ? step : N - 1 - step;
-    int f = dir * Hd + j;
-    int hh = f / C, c = f % C;
-    float go = dQPOS[((long long)b * Himg * Wd + (long long)hh * Wd + w) * C + c] + DH[i];
-    long long gi = ((((long long)step * 2 + dir) * Wd + w) * 4) * Hd + j;
-    float rr = GATES[gi], zz = GATES[gi + Hd], nn = GATES[gi + 2 * Hd], ghn = GATES[gi + 3 * Hd];
-    float hp = HALL[(((long long)dir * (N + 1) + step) * Wd + w) * Hd + j];
-    float dn = go * (1.f - zz);
-    float dz = go * (hp - nn);
-    float dpn = dn * (1.f - nn * nn);
-    float dpr = dpn * ghn * rr * (1.f - rr);
-    float dpz = dz * zz * (1.f - zz);
-    long long g3 = ((long long)dir * Wd + w) * 3 * Hd + j;
-    DGISUM[g3] += dpr;
-    DGISUM[g3 + Hd] += dpz;
-    DGISUM[g3 + 2 * Hd] += dpn;
-    long long d3 = ((((long long)dir * N + step) * Wd + w) * 3) * Hd + j;
-    DGH[d3] = dpr;
-    DGH[d3 + Hd] = dpz;
-    DGH[d3 + 2 * Hd] = dpn * rr;
-    if (DGHPL) {
-      split_bf16(dpr, DGHPL, DGHPL + plane_lo, d3);
-      split_bf16(dpz, DGHPL, DGHPL + plane_lo, d3 + Hd);
-      split_bf16(dpn * rr, DGHPL, DGHPL + plane_lo, d3 + 2 * Hd);
+  const int Hd4 = Hd >> 2;
+  const int n4 = 2 * Wd * Hd4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int j = (i % Hd4) << 2;
+    const int r = i / Hd4;
+    const int w = r % Wd, dir = r / Wd;
+    const int b = dir == 0 ? step : N - 1 - step;
+    const int f = dir * Hd + j;
+    const int hh = f / C, c = f % C;
+    const long long e = (long long)r * Hd + j;          // element index in DH
+    const long long gi = ((((long long)step * 2 + dir) * Wd + w) * 4) * Hd + j;
+    const long long g3 = ((long long)dir * Wd + w) * 3 * Hd + j;
+    const long long d3 = ((((long long)dir * N + step) * Wd + w) * 3) * Hd + j;
+    float dq[4], dh[4], rr[4], zz[4], nn[4], ghn[4], hp[4], sr[4], sz[4], sn[4];
+    ld4(dQPOS + ((long long)b * Himg * Wd + (long long)hh * Wd + w) * C + c, dq);
+    ld4(DH + e, dh);
+    ld4(GATES + gi, rr); ld4(GATES + gi + Hd, zz); ld4(GATES + gi + 2 * Hd, nn); ld4(GATES + gi + 3 * Hd, ghn);
+    ld4(HALL + (((long long)dir * (N + 1) + step) * Wd + w) * Hd + j, hp);
+    ld4(DGISUM + g3, sr); ld4(DGISUM + g3 + Hd, sz); ld4(DGISUM + g3 + 2 * Hd, sn);
+    float dpr[4], dpz[4], dpn[4], dhn[4], carry[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float go = dq[k] + dh[k];
+      const float dn = go * (1.f - zz[k]);
+      const float dz = go * (hp[k] - nn[k]);
+      dpn[k] = dn * (1.f - nn[k] * nn[k]);
+      dpr[k] = dpn[k] * ghn[k] * rr[k] * (1.f - rr[k]);
+      dpz[k] = dz * zz[k] * (1.f - zz[k]);
+      dhn[k] = dpn[k] * rr[k];
+      carry[k] = go * zz[k];
+      sr[k] += dpr[k]; sz[k] += dpz[k]; sn[k] += dpn[k];
     }
-    DH[i] = go * zz;
+    st4(DGISUM + g3, sr); st4(DGISUM + g3 + Hd, sz); st4(DGISUM + g3 + 2 * Hd, sn);
+    st4(DGH + d3, dpr); st4(DGH + d3 + Hd, dpz); st4(DGH + d3 + 2 * Hd, dhn);
+    if (DGHPL) {
+      split4_store(dpr, DGHPL, DGHPL + plane_lo, d3);
+      split4_store(dpz, DGHPL, DGHPL + plane_lo, d3 + Hd);
+      split4_store(dhn, DGHPL, DGHPL + plane_lo, d3 + 2 * Hd);
+    }
+    st4(DH + e, carry);
   }
 }
 
@@ -425,8 +454,9 @@ int tatt_rpe_scatter(const float* dX, float* demb, int H, int W, int C, void* st
 int tatt_rpe_gate_fwd(const float* GI, const float* GH, float* HALL, float* GATES, float* QPOS, void* HPL,
                       long long plane_lo, int step, int N, int Wd, int Hd, int C, int Himg, void* stream) {
   TATT_REQUIRE(2 * Hd == Himg * C, "rpe_gate_fwd: 2*Hd (%d) must equal Himg*C (%d)", 2 * Hd, Himg * C);
-  long long n = 2LL * Wd * Hd;
-  rpe_gate_fwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(GI, GH, HALL, GATES, QPOS,
+  TATT_REQUIRE(Hd % 4 == 0 && C % 4 == 0, "rpe_gate_fwd: Hd (%d) and C (%d) must be multiples of 4", Hd, C);
+  long long n = 2LL * Wd * (Hd / 4);
+  rpe_gate_fwd_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(GI, GH, HALL, GATES, QPOS,
                                                                                 (__nv_bfloat16*)HPL, plane_lo, step, N,
                                                                                 Wd, Hd, C, Himg);
   TATT_LAUNCH_CHECK("rpe_gate_fwd_kernel");
@@ -436,8 +466,9 @@ int tatt_rpe_gate_bwd(const float* dQPOS, const float* HALL, const float* GATES,
                       float* DGH, void* DGHPL, long long plane_lo, int step, int N, int Wd, int Hd, int C, int Himg,
                       void* stream) {
   TATT_REQUIRE(2 * Hd == Himg * C, "rpe_gate_bwd: 2*Hd (%d) must equal Himg*C (%d)", 2 * Hd, Himg * C);
-  long long n = 2LL * Wd * Hd;
-  rpe_gate_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dQPOS, HALL, GATES, DH, DGISUM, DGH,
+  TATT_REQUIRE(Hd % 4 == 0 && C % 4 == 0, "rpe_gate_bwd: Hd (%d) and C (%d) must be multiples of 4", Hd, C);
+  long long n = 2LL * Wd * (Hd / 4);
+  rpe_gate_bwd_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dQPOS, HALL, GATES, DH, DGISUM, DGH,
                                                                                 (__nv_bfloat16*)DGHPL, plane_lo,
                                                                                 step, N, Wd, Hd, C, Himg);
   TATT_LAUNCH_CHECK("rpe_gate_bwd_kernel");
