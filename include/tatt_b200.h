@@ -73,7 +73,10 @@ int tatt_rows_wgrad(const float* A, long long lda, int a_off0, int a_off1, const
 /* ---- convolution (stride 1), implicit GEMM over NHWC: nn.Conv2d ------------------------------------
  * model/tsrn.py:597 (9x9 stem), 876,884 (SRB 3x3), 611 (block7), 1043 (upsample 64->256), 623 (9x9 out);
  * model/stn_head.py:15.  Weights are first packed to Wt[(ky,kx,ci)][co] (flip=0) or, for the
- * data-gradient, to the flipped/transposed Wt[(ky,kx,co)][ci] (flip=1). */
+ * data-gradient, to the flipped/transposed Wt[(ky,kx,co)][ci] (flip=1).
+ * flags of tatt_conv2d_igemm / tatt_conv2d_wgrad: 1 / 2 / 128 / 1024 as for tatt_gemm; 2048: the bf16 planes of X at the start of
+ * `ws` are still valid from an earlier call on the same X (forward -> weight gradient, or the dY planes the weight-gradient
+ * pass leaves behind the X planes -> data gradient with ws advanced past the X planes): skip the split pass. */
 int tatt_conv_weight_pack(const float* W, float* Wt, int Cout, int Cin, int KH, int KW, int CinP, int CoutP,
                           int flip, void* stream);
 int tatt_conv_weight_unpack_grad(const float* dWt, float* dW, int Cout, int Cin, int KH, int KW, int CinP,
