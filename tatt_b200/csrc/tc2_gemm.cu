@@ -756,7 +756,8 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
     int maxsk = ceil_div(p.K, BK * 4);
     if (sk > maxsk) sk = maxsk;
   } else if (tiles < 74 && p.K >= 512 && !(q.flags & F_RELU)) {
-    sk = (int)((148 + tiles - 1) / tiles);
+    sk = (int)(148 / tiles);            // at most one CTA per SM: a partial second wave would double the tail SMs' time
+    if (sk < 1) sk = 1;
     int maxsk = p.K / 256;
     if (sk > maxsk) sk = maxsk;
     if (sk > 1) {
