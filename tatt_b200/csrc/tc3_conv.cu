@@ -287,11 +287,13 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
 constexpr int RL_NSTAGE = 4;                                  // weight-tap ring (4 x 16 KB) + 16 KB of epilogue staging
 constexpr int RL_STG_BYTES = 4 * 32 * 128;                    // per epilogue warp: [32 px][32 ch] fp32
 
-template <bool single>
+template <bool single, bool cat>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                     float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles, int dbg) {
+  constexpr uint32_t acc_stride = cat ? 256u : 128u, row_stride = cat ? 128u : 64u;
+  constexpr uint32_t tmem_cols = cat ? 512u : 256u;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) unsigned long long pair_full[2], pair_empty[2], w_full[RL_NSTAGE], w_empty[RL_NSTAGE], acc_full[2],
@@ -320,7 +322,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   __syncwarp();
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"(256u)
+                 "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -328,6 +330,10 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  // cat: the weight tap is ONE [128 x 64] K-major tile (rows 0..63 = hi plane, 64..127 = lo plane, contiguous in the
+  // ring), so A_hi x [B_hi | B_lo] is a single N = 128 MMA into two 64-column blocks (hi*hi | hi*lo) and A_lo x B_hi a
+  // second, N = 64 one: 14 KB of shared-memory operand fetch per k-step and row instead of 18 KB, 2 issues instead of
+  // 3.  The epilogue adds the two column blocks.  Accumulators: 2 rows x 128 columns, ping-pong = all 512 TMEM columns.
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -374,6 +380,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     // ------------------------------------------------------------ MMA issuer
     {                                             // whole warp, uniform control flow; one elected lane issues
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint32_t LBO1 = 1u << 16;
       int nfull0 = 0, nfull1 = 0;                 // pair loads consumed
       int ws = 0;
@@ -399,7 +406,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           rowh[j] = ((a_hi + off) >> 4) | LBO1;
           rowl[j] = ((a_lo + off) >> 4) | LBO1;
         }
-        const uint32_t tacc = tmem_base + (uint32_t)((it & 1) * 128);
+        const uint32_t tacc = tmem_base + (uint32_t)(it & 1) * acc_stride;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap % 3;
@@ -419,12 +426,16 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
               const uint32_t acc = (tap > 0 || k16 > 0) ? 1u : 0u;
-              if (!single) {
-                umma_lo_elect(tacc + (uint32_t)(r * 64), al + 2 * k16, bh + 2 * k16, idesc, acc);
-                umma_lo_elect(tacc + (uint32_t)(r * 64), ah + 2 * k16, bl + 2 * k16, idesc, 1u);
-                umma_lo_elect(tacc + (uint32_t)(r * 64), ah + 2 * k16, bh + 2 * k16, idesc, 1u);
+              const uint32_t tm = tacc + (uint32_t)r * row_stride;
+              if (cat) {
+                umma_lo_elect(tm, ah + 2 * k16, bh + 2 * k16, idesc128, acc);   // [hi*hi | hi*lo]
+                umma_lo_elect(tm, al + 2 * k16, bh + 2 * k16, idesc, 1u);       // lo*hi
+              } else if (!single) {
+                umma_lo_elect(tm, al + 2 * k16, bh + 2 * k16, idesc, acc);
+                umma_lo_elect(tm, ah + 2 * k16, bl + 2 * k16, idesc, 1u);
+                umma_lo_elect(tm, ah + 2 * k16, bh + 2 * k16, idesc, 1u);
               } else {
-                umma_lo_elect(tacc + (uint32_t)(r * 64), ah + 2 * k16, bh + 2 * k16, idesc, acc);
+                umma_lo_elect(tm, ah + 2 * k16, bh + 2 * k16, idesc, acc);
               }
             }
           }
@@ -464,7 +475,15 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 #pragma unroll
           for (int c16 = 0; c16 < 2; ++c16) {
             uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((it & 1) * 128 + r * 64 + h * 32 + c16 * 16), v);
+            const uint32_t tcol = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(it & 1) * acc_stride +
+                                  (uint32_t)r * row_stride + (uint32_t)(h * 32 + c16 * 16);
+            tmem_ld16(tcol, v);
+            if (cat) {                              // + the hi*lo column block
+              uint32_t v2[16];
+              tmem_ld16(tcol + 64, v2);
+#pragma unroll
+              for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(v2[q]));
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               *reinterpret_cast<float4*>(stg + lane * 128 + (((4 * c16 + q) ^ (lane & 7)) << 4)) =
@@ -490,7 +509,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -722,12 +741,19 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
       const char* e = getenv("TATT_ROLL_DBG");
       return e ? atoi(e) : 0;
     }();
+    static const int cat_on = []() {               // TATT_ROLL_CAT=0: three N = 64 MMAs per k-step instead of N = 128 + N = 64
+      const char* e = getenv("TATT_ROLL_CAT");
+      return e ? atoi(e) : 1;
+    }();
     if (single) {
-      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
+      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      conv3x3_roll_kernel<true, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
+    } else if (cat_on) {
+      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      conv3x3_roll_kernel<false, true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
     } else {
-      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
+      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      conv3x3_roll_kernel<false, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
     }
     TATT_LAUNCH_CHECK("conv3x3_roll_kernel");
     return 0;
