@@ -169,15 +169,15 @@ def conv_roofline(dev, batch, h, w, peaks):
     traffic = NCU_CONV_TRAFFIC_BYTES if (batch, h, w) == (64, 32, 128) else None
     bf16 = bool(ops._precision_flag & ops.F_BF16)
     return {"bound": "tensor", "kernel": "split_dense_kernel + conv3x3_roll_kernel (conv3x3 64->64, NHWC; persistent "
-            "rolling-halo TMA tiles + TMA weight ring, tcgen05 kind::f16 with a bf16 hi/lo operand split, 3 MMAs per "
-            "k-step, ping-pong fp32 TMEM accumulators)",
+            "rolling-halo TMA tiles + TMA weight ring, tcgen05 kind::f16 with a bf16 hi/lo operand split: A_hi x [B_hi|B_lo] "
+            "(N=128) + A_lo x B_hi (N=64) per k-step, ping-pong fp32 TMEM accumulators)",
             "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak,
             "traffic": traffic, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if "bf16_tflops" in peaks
             else "fallback 1.59 PFLOP/s, of fallback", "launch_ms": t * 1e3, "algorithmic_flops_per_launch": flops,
             "kernel_only_ms": tk * 1e3, "kernel_only_tflops": flops / tk / 1e12, "kernel_only_frac": flops / tk / 1e12 / peak,
             "note": ("bf16 mode: one MMA per product" if bf16 else
-                     "fp32-parity mode costs 3 bf16 MMAs per product (ceiling = 1/3 of the bf16 peak); at N = 64 the "
-                     "MMAs are bound by shared-memory operand fetch (~80 cycles each vs the 32-cycle math floor)")}
+                     "fp32-parity mode costs 3 bf16 products per MAC (ceiling = 1/3 of the bf16 peak); with C_out = 64 "
+                     "the MMAs are bound by shared-memory operand fetch, not by the tensor-pipe math rate")}
 
 
 def run_ours(args):

@@ -737,10 +737,16 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const int grid = ntiles < nsm ? ntiles : nsm;
+    // timing-experiment switches of the kernel (1: skip the global stores, 2: load the weight taps once) produce WRONG
+    // results by design; they are reachable only in builds with -DTATT_ROLL_EXPERIMENTS
+#ifdef TATT_ROLL_EXPERIMENTS
     static const int dbg = []() {
       const char* e = getenv("TATT_ROLL_DBG");
       return e ? atoi(e) : 0;
     }();
+#else
+    const int dbg = 0;
+#endif
     static const int cat_on = []() {               // TATT_ROLL_CAT=0: three N = 64 MMAs per k-step instead of N = 128 + N = 64
       const char* e = getenv("TATT_ROLL_CAT");
       return e ? atoi(e) : 1;
