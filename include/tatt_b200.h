@@ -189,6 +189,16 @@ int tatt_adam_clip_step(float* p, const float* g, float* m, float* v, long long 
 int tatt_memcpy_d2d(void* dst, const void* src, long long bytes, void* stream);
 int tatt_memset0(void* dst, long long bytes, void* stream);
 
+/* ---- image loss directly after the path: loss/image_loss.py:10-58 ----------------------
+ * ImageLoss(gradient=True, loss_weight=[w0, w1]) on NCHW fp32 images with C >= 3 channels:
+ * loss[n] = w0 * mean (out - tgt)^2 + w1 * mean_{RGB} |gradmag(out) - gradmag(tgt)|  (central differences, zero
+ * padding, eps 1e-6).  G (optional, [N][3][H][W][2] floats) receives the per-pixel gradient-magnitude derivatives the
+ * backward pass gathers; ws: >= 2*N doubles.  bwd: dout = gloss[n] * d loss[n] / d out. */
+int tatt_image_loss_fwd(const float* out, const float* tgt, float* loss, float* G, int N, int C, int H, int W, float w0,
+                        float w1, void* ws, void* stream);
+int tatt_image_loss_bwd(const float* out, const float* tgt, const float* G, const float* gloss, float* dout, int N, int C,
+                        int H, int W, float w0, float w1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,3 +68,41 @@ def test_psnr_formula():
     a = torch.rand(1, 4, 8, 8)
     assert orc.psnr(a, a) == float("inf")
     assert abs(orc.psnr(a, a + 1.0 / 255) - 20 * torch.log10(torch.tensor(255.0)).item()) < 1e-3
+
+
+# ---------------------------------------------------------------------------------- loss block
+def test_loss_oracle_matches_reference_fixture():
+    """oracle/loss_oracle.py vs the fixture generated from the live `loss/image_loss.py:ImageLoss` (bit-exact)"""
+    import os
+    from oracle import loss_oracle as lo
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "image_loss_n3.pt"))
+    o = fx["out"].clone().requires_grad_(True)
+    loss = lo.image_loss(o, fx["target"])
+    (loss.mean() * 100).backward()
+    assert torch.equal(loss, fx["loss"]) and torch.equal(o.grad, fx["dout"])
+    assert o.grad[0, :3, 4, 6].abs().max().item() < 1e-3            # flat patch: only the MSE term (zero there) acts
+    o64 = fx["out"].double().requires_grad_(True)
+    lo.training_scalar(o64, fx["target"].double()).backward()
+    assert torch.allclose(o64.grad, fx["dout64"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.skipif(not rh.available(), reason="live reference not present (build container only)")
+def test_loss_oracle_bit_exact_vs_live_reference():
+    import importlib
+    import warnings
+    from oracle import loss_oracle as lo
+    rh.load()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = importlib.import_module("loss.image_loss")
+        crit = mod.ImageLoss(gradient=True, loss_weight=[20, 1e-4])
+    g = torch.Generator().manual_seed(5)
+    out = torch.tanh(torch.randn(2, 4, 9, 21, generator=g)).requires_grad_(True)
+    tgt = torch.rand(2, 4, 9, 21, generator=g)
+    l_ref = crit(out, tgt)
+    (l_ref.mean() * 100).backward()
+    g_ref = out.grad.clone()
+    out.grad = None
+    l_o = lo.image_loss(out, tgt)
+    (l_o.mean() * 100).backward()
+    assert torch.equal(l_ref, l_o) and torch.equal(g_ref, out.grad)
