@@ -96,3 +96,22 @@ def test_no_cpu_fallback():
         net(torch.rand(1, 4, 16, 64))
     with pytest.raises(RuntimeError, match="parameter container"):
         net.block2.gru1(torch.rand(1, 64, 4, 4))
+
+
+def test_image_loss_surface_cpu():
+    """`tatt_b200.losses.ImageLoss` mirrors `loss/image_loss.py:ImageLoss`: constructor, broken gradient=False path
+    (UnboundLocalError in the reference, image_loss.py:32), and no CPU fallback."""
+    import inspect
+
+    import pytest
+    import torch
+    from tatt_b200.losses import ImageLoss
+    sig = inspect.signature(ImageLoss.__init__)
+    assert list(sig.parameters)[1:] == ["gradient", "loss_weight"]
+    assert sig.parameters["gradient"].default is True and list(sig.parameters["loss_weight"].default) == [20, 1e-4]
+    assert list(inspect.signature(ImageLoss.forward).parameters)[1:] == ["out_images", "target_images", "grad_mask"]
+    x = torch.zeros(2, 4, 8, 8)
+    with pytest.raises(UnboundLocalError):
+        ImageLoss(gradient=False)(x, x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ImageLoss()(x, x)
