@@ -106,3 +106,59 @@ def test_loss_oracle_bit_exact_vs_live_reference():
     l_o = lo.image_loss(out, tgt)
     (l_o.mean() * 100).backward()
     assert torch.equal(l_ref, l_o) and torch.equal(g_ref, out.grad)
+
+
+# ---------------------------------------------------------------------------------- CRNN text-prior generator
+def _crnn_sd(training):
+    from oracle import crnn_oracle as co
+    sd = co.make_state_dict(1234)
+    co.perturb_bn_(sd, 1235)
+    sd = {k: v.detach().clone() for k, v in sd.items()}
+    if training:
+        for k, v in sd.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+    return sd
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_crnn_oracle_matches_reference_fixture(training):
+    """oracle/crnn_oracle.py (state-dict functional CRNN + parse_crnn_data) vs the fixture generated from the live
+    `model/crnn/crnn.py:CRNN(32, 1, 37, 256)`: logits, sampled gradients and BN buffers bit-exact"""
+    import os
+    from oracle import crnn_oracle as co
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "crnn_n3.pt"))
+    sd = _crnn_sd(training)
+    x = torch.rand(3, 3, 16, 64, generator=torch.Generator().manual_seed(1234))
+    gray = co.parse_crnn_data(x)
+    assert torch.equal(gray, fx["gray"])
+    logits = co.crnn_forward(sd, gray, training)
+    assert torch.equal(logits, fx["train_logits" if training else "eval_logits"])
+    tp = co.text_prior(logits)
+    assert tuple(tp.shape) == (3, 37, 1, 26) and torch.allclose(tp.sum(1), torch.ones(3, 1, 26), atol=1e-5)
+    if training:
+        gen = torch.Generator().manual_seed(99)
+        (logits * torch.randn(logits.shape, generator=gen)).sum().backward()
+        for n, ref in fx["train_grads"].items():
+            assert tuple(sd[n].grad.shape) == tuple(ref["shape"]), n
+            assert torch.equal(sd[n].grad.reshape(-1)[ref["idx"]], ref["val"]), n
+            assert abs(sd[n].grad.double().sum().item() - ref["sum"]) <= 1e-6 * max(1.0, abs(ref["sum"])), n
+        for n, b in fx["train_buffers"].items():
+            assert torch.equal(sd[n], b), n
+
+
+@pytest.mark.skipif(not rh.available(), reason="live reference not present (build container only)")
+def test_crnn_state_dict_matches_live_reference():
+    import importlib
+    import warnings
+    from oracle import crnn_oracle as co
+    rh.load()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = importlib.import_module("model.crnn.crnn")
+    torch.manual_seed(77)
+    ref_sd = mod.CRNN(32, 1, 37, 256).state_dict()
+    sd = co.make_state_dict(77)
+    assert list(ref_sd.keys()) == list(sd.keys())
+    for k in ref_sd:
+        assert torch.equal(ref_sd[k], sd[k]), k
