@@ -48,6 +48,36 @@ def main():
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "image_loss_n3.pt")
     torch.save(fx, path)
     print("wrote", path, "loss", loss.tolist())
+    loss_block()
+
+
+def loss_block():
+    """SemanticLoss / TRI_SSIM / torch_rotate_img outputs of the live reference -> loss_block_n3.pt"""
+    import ast
+    import importlib
+    import warnings
+    import torch.nn.functional as F
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sl = importlib.import_module("loss.semantic_loss")
+        sp = importlib.import_module("utils.ssim_psnr")
+        g = torch.Generator().manual_seed(1234)
+        p = torch.softmax(torch.randn(26, 3, 37, generator=g), -1)
+        q = torch.softmax(torch.randn(26, 3, 37, generator=g), -1)
+        a, b, c = [torch.rand(3, 4, 16, 40, generator=g) for _ in range(3)]
+        arcs = (torch.rand(3, generator=g) - 0.5) * 0.2
+        offs = torch.rand(3, generator=g)
+        src = open(os.path.join(rh.REF_ROOT, "interfaces", "super_resolution.py")).read()
+        fn = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "torch_rotate_img"][0]
+        ns = {"torch": torch, "F": F}
+        exec(compile(ast.Module(body=[fn], type_ignores=[]), "torch_rotate_img", "exec"), ns)
+        fx = {"pred": p, "gt": q, "semantic": sl.SemanticLoss()(p, q).clone(), "a": a, "b": b, "c": c,
+              "tri_ssim": sp.TRI_SSIM()(a, b, c).clone(), "tri_ssim_per_sample": sp.TRI_SSIM(size_average=False)(a, b, c).clone(),
+              "arcs": arcs, "offs": offs, "rotated": ns["torch_rotate_img"](None, a, arcs, offs).clone(),
+              "torch": str(torch.__version__)}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "loss_block_n3.pt")
+    torch.save(fx, path)
+    print("wrote", path, os.path.getsize(path))
 
 
 if __name__ == "__main__":
