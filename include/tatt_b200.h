@@ -180,6 +180,9 @@ int tatt_tps_sample_bwd(const float* X, const float* ctrl, const float* invK, co
 
 /* ---- gradient step on a flat buffer: clip_grad_norm_(0.25) + Adam, interfaces/super_resolution.py:1083-1085 */
 int tatt_sqnorm(const float* x, long long n, float* out, int zero_first, void* stream);
+/* gradient packing in one launch: table = DEVICE array of nchunks x {source address, destination offset (floats),
+ * count (floats, <= 16384)}; sq (optional) receives sum(x^2) over everything copied (zeroed first) */
+int tatt_multi_copy(const unsigned long long* table, int nchunks, float* dst, float* sq, void* stream);
 /* step_state: DEVICE {unused, step>=1} (advance it with tatt_rng_advance before the call) */
 int tatt_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, const float* sqnorm,
                         float max_norm, float lr, float beta1, float beta2, float eps,

@@ -241,6 +241,47 @@ __global__ void sqnorm_kernel(const float* __restrict__ x, long long n, float* _
   }
 }
 
+// Gradient packing as ONE launch: chunk c copies tab[3c+2] floats from address tab[3c] to dst + tab[3c+1]
+// (chunks are <= 16384 floats; 16-byte aligned sources take the float4 path) and, when sq != nullptr, adds the
+// chunk's sum of squares to sq[0] (the global-norm numerator of clip_grad_norm_ for a single-rank step).
+__global__ void multi_copy_kernel(const unsigned long long* __restrict__ tab, float* __restrict__ dst,
+                                  float* __restrict__ sq) {
+  __shared__ float red[8];
+  const unsigned long long* e = tab + 3ull * blockIdx.x;
+  const float* __restrict__ src = (const float*)e[0];
+  float* __restrict__ out = dst + e[1];
+  const int n = (int)e[2];
+  float s = 0.f;
+  if (((e[0] | (unsigned long long)(uintptr_t)out) & 15ull) == 0) {
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = ((const float4*)src)[i];
+      ((float4*)out)[i] = v;
+      s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      const float v = src[i];
+      out[i] = v;
+      s = fmaf(v, v, s);
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = src[i];
+      out[i] = v;
+      s = fmaf(v, v, s);
+    }
+  }
+  if (sq == nullptr) return;
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(sq, t);
+  }
+}
+
 // Fused global-norm clip + Adam on a flat fp32 buffer (super_resolution.py:1083-1085, base.py:557-558).
 // sqnorm[0] holds sum(g^2) over the whole buffer (already all-reduced and averaged grads).
 __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -399,6 +440,16 @@ int tatt_sqnorm(const float* x, long long n, float* out, int zero_first, void* s
   if (n <= 0) return 0;
   sqnorm_kernel<<<ew_blocks(n, 2048), 256, 0, st>>>(x, n, out);
   TATT_LAUNCH_CHECK("sqnorm_kernel");
+  return 0;
+}
+
+int tatt_multi_copy(const unsigned long long* table, int nchunks, float* dst, float* sq, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sq != nullptr) TATT_CUDA(cudaMemsetAsync(sq, 0, sizeof(float), st));
+  if (nchunks <= 0) return 0;
+  TATT_REQUIRE(table != nullptr && dst != nullptr, "multi_copy: null table / destination");
+  multi_copy_kernel<<<nchunks, 256, 0, st>>>(table, dst, sq);
+  TATT_LAUNCH_CHECK("multi_copy_kernel");
   return 0;
 }
 

@@ -47,6 +47,20 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Bumped whenever parameters are updated through raw pointers (the fused clip+Adam kernel writes the flat parameter
+# buffer without touching torch's version counters); caches derived from weights key on it (tsrn.TPInterpreter).
+_weights_epoch = 0
+
+
+def weights_epoch() -> int:
+    return _weights_epoch
+
+
+def bump_weights_epoch() -> None:
+    global _weights_epoch
+    _weights_epoch += 1
+
+
 def _p(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -56,6 +70,10 @@ def _chk(t: Tensor, name: str = "tensor") -> Tensor:
         raise RuntimeError("tatt_b200: %s must be a CUDA tensor (the hot path has no CPU fallback)" % name)
     if t.dtype != torch.float32:
         raise RuntimeError("tatt_b200: %s must be float32, got %s" % (name, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError("tatt_b200: %s lives on %s but the current device is cuda:%d; kernels launch on the current "
+                           "device's stream -- wrap the call in torch.cuda.device(...)" % (
+                               name, t.device, torch.cuda.current_device()))
     return t
 
 
@@ -647,7 +665,12 @@ class DeviceRNG:
     def get(cls, device: torch.device) -> "DeviceRNG":
         key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
         if key not in cls._per_device:
-            cls._per_device[key] = DeviceRNG(device, torch.initial_seed() if cls._seed is None else cls._seed)
+            seed = cls._seed
+            if seed is None:        # default: torch's seed, decorrelated across data-parallel ranks
+                import torch.distributed as dist
+                rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+                seed = torch.initial_seed() + 0x9E3779B97F4A7C15 * rank
+            cls._per_device[key] = DeviceRNG(device, seed)
         return cls._per_device[key]
 
     @classmethod

@@ -158,6 +158,10 @@ class Tape:
         x2 = x.view(-1, C)
         use_batch = training or bn.running_mean is None
         if use_batch:
+            if bn.momentum is None and training and bn.running_mean is not None:
+                # torch: cumulative moving average 1/num_batches_tracked (a host-side value; nothing on this path
+                # constructs such a BatchNorm, so it is not a device-resident / graph-safe quantity)
+                raise NotImplementedError("tatt_b200: BatchNorm(momentum=None) (cumulative average) is not supported")
             mean, invstd = ops.bn_stats(x2, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
                                         bn.running_mean if training else None, bn.running_var if training else None)
             if training and bn.num_batches_tracked is not None:

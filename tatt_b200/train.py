@@ -57,6 +57,33 @@ class GradBucket:
             self.flat_grad[o:o + p.numel()].copy_(p.grad.reshape(-1))
         return self.flat_grad
 
+    CHUNK = 16384
+
+    def pack_cuda(self, sq: Optional[Tensor] = None) -> Tensor:
+        """The same packing as ONE kernel launch (tatt_multi_copy) instead of one memcpy per parameter: a table of
+        {source address, destination offset, count} chunks is staged through pinned host memory (graph replays re-read
+        it; addresses inside a captured graph's private pool are stable).  `sq` (1 float) receives sum(g^2)."""
+        from . import _cabi, ops
+        rows = []
+        for p, o in zip(self.params, self.offsets):
+            g = p.grad
+            if g is None:
+                raise RuntimeError("parameter of the gradient bucket has no gradient this step")
+            if not g.is_contiguous():
+                g = g.contiguous()
+                p.grad = g
+            base, n = g.data_ptr(), p.numel()
+            for c in range(0, n, self.CHUNK):
+                rows.append((base + 4 * c, o + c, min(self.CHUNK, n - c)))
+        if getattr(self, "_tab_host", None) is None or self._tab_host.shape[0] != len(rows):
+            self._tab_host = torch.empty(len(rows), 3, dtype=torch.int64).pin_memory()
+            self._tab_dev = torch.empty(len(rows), 3, dtype=torch.int64, device=self.flat_grad.device)
+        self._tab_host.copy_(torch.tensor(rows, dtype=torch.int64))
+        self._tab_dev.copy_(self._tab_host, non_blocking=True)
+        _cabi.call("tatt_multi_copy", self._tab_dev.data_ptr(), len(rows), self.flat_grad.data_ptr(),
+                   None if sq is None else sq.data_ptr(), ops._stream())
+        return self.flat_grad
+
     def allreduce_mean(self, group=None) -> Tensor:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
@@ -99,22 +126,55 @@ class Trainer:
         if self.world > 1:
             dist.all_reduce(self.bucket.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
 
+    def _pack(self) -> None:
+        """Gradients -> flat bucket in one launch; on a single rank the same pass also yields sum(g^2)."""
+        self._ensure_bucket().pack_cuda(self.sq if self.world == 1 else None)
+
     def _update_kernels(self) -> None:
-        """sum(g^2) of the SUMMED gradient, then clip + Adam; the 1/world averaging is folded in."""
+        """sum(g^2) of the SUMMED gradient (already produced by the packing pass on one rank), then clip + Adam;
+        the 1/world averaging is folded in."""
         from . import _cabi, ops
         b, st = self.bucket, ops._stream()
         g = b.flat_grad
-        _cabi.call("tatt_sqnorm", g.data_ptr(), b.numel, self.sq.data_ptr(), 1, st)
+        for p, o in zip(b.params[:4], b.offsets[:4]):          # cheap guard against re-assigned p.data (model.to(), ...)
+            if p.data_ptr() != b.flat_param.data_ptr() + 4 * o:
+                raise RuntimeError("a parameter was re-assigned after the Trainer flattened it (model.to()/.float()/"
+                                   "load with assign=True?); rebuild the Trainer")
+        if self.world > 1:
+            _cabi.call("tatt_sqnorm", g.data_ptr(), b.numel, self.sq.data_ptr(), 1, st)
         _cabi.call("tatt_rng_advance", self.step_state.data_ptr(), st)
         _cabi.call("tatt_adam_clip_step", b.flat_param.data_ptr(), g.data_ptr(), self.m.data_ptr(),
                    self.v.data_ptr(), b.numel, self.sq.data_ptr(), self.max_norm, self.lr, self.betas[0],
                    self.betas[1], self.eps, self.step_state.data_ptr(), 1.0 / self.world, st)
+        ops.bump_weights_epoch()          # raw-pointer update: invalidate weight-derived caches (eval qpos)
 
     def optimizer_step(self) -> Tensor:
-        self._ensure_bucket().pack()
+        self._pack()
         self._allreduce()
         self._update_kernels()
         return self.sq
+
+    # ---- resume support: Adam moments + step counter (parameters / BN buffers are in model.state_dict())
+    def state_dict(self) -> dict:
+        if self.bucket is None:
+            return {"step": 0, "exp_avg": {}, "exp_avg_sq": {}}
+        b = self.bucket
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        m = {names[id(p)]: self.m[o:o + p.numel()].view(p.shape).clone() for p, o in zip(b.params, b.offsets)}
+        v = {names[id(p)]: self.v[o:o + p.numel()].view(p.shape).clone() for p, o in zip(b.params, b.offsets)}
+        return {"step": int(self.step_state[1].item()), "exp_avg": m, "exp_avg_sq": v}
+
+    def load_state_dict(self, sd: dict) -> None:
+        """Needs the bucket layout, i.e. call after at least one forward_backward (or pass a model whose
+        parameters all have .grad); restores Adam's exp_avg / exp_avg_sq / step."""
+        b = self._ensure_bucket()
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        for p, o in zip(b.params, b.offsets):
+            n = names[id(p)]
+            if n in sd["exp_avg"]:
+                self.m[o:o + p.numel()].copy_(sd["exp_avg"][n].reshape(-1))
+                self.v[o:o + p.numel()].copy_(sd["exp_avg_sq"][n].reshape(-1))
+        self.step_state[1] = int(sd["step"])
 
     def step(self, x: Tensor, text_emb: Optional[Tensor], grad_out: Tensor):
         out = self.forward_backward(x, text_emb, grad_out)
@@ -137,7 +197,34 @@ class GraphedTrainer(Trainer):
         self.graph_fb = self.graph_opt = None
         self.out: Optional[Tensor] = None
 
+    def _snapshot(self):
+        """Everything a training step mutates: parameters, BN buffers, Adam state, step counter, dropout RNG."""
+        from .ops import DeviceRNG
+        dev = self.x.device
+        snap = {"params": [p.detach().clone() for p in self.model.parameters()],
+                "buffers": [b.detach().clone() for b in self.model.buffers()],
+                "rng": DeviceRNG.get(dev).state.clone()}
+        if self.bucket is not None:
+            snap.update(m=self.m.clone(), v=self.v.clone(), step=self.step_state.clone())
+        return snap
+
+    def _restore(self, snap) -> None:
+        from .ops import DeviceRNG
+        with torch.no_grad():
+            for p, s in zip(self.model.parameters(), snap["params"]):
+                p.copy_(s)
+            for b, s in zip(self.model.buffers(), snap["buffers"]):
+                b.copy_(s)
+            DeviceRNG.get(self.x.device).state.copy_(snap["rng"])
+            if "m" in snap:
+                self.m.copy_(snap["m"]); self.v.copy_(snap["v"]); self.step_state.copy_(snap["step"])
+            else:
+                self.m.zero_(); self.v.zero_(); self.step_state.zero_()
+
     def capture(self, warmup: int = 2) -> None:
+        """Warm-up steps run on whatever is in the static input buffers and are ROLLED BACK afterwards (weights, BN
+        running statistics, Adam moments, step counter, dropout stream), so capturing has no training side effect."""
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -148,24 +235,32 @@ class GraphedTrainer(Trainer):
         self.graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_fb):
             self.out = self.forward_backward(self.x, self.text, self.grad_out)
-            self.bucket.pack()
-        self.graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
-            self._update_kernels()
+            self._pack()
+            if self.world == 1:                   # no collective in between: one graph for the whole step
+                self._update_kernels()
+        if self.world > 1:
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
+                self._update_kernels()
+        torch.cuda.synchronize()
+        self._restore(snap)                        # capture itself does not execute, but the warm-up did
 
     def step(self, x: Optional[Tensor] = None, text_emb: Optional[Tensor] = None, grad_out: Optional[Tensor] = None):
         """Inputs may live on the host (pinned) or the device; None -> reuse the static buffers."""
-        if self.graph_fb is None:
-            self.capture()
         if x is not None and x is not self.x:
             self.x.copy_(x, non_blocking=True)
         if text_emb is not None and text_emb is not self.text:
             self.text.copy_(text_emb, non_blocking=True)
         if grad_out is not None and grad_out is not self.grad_out:
             self.grad_out.copy_(grad_out, non_blocking=True)
+        if self.graph_fb is None:
+            self.capture()
         self.graph_fb.replay()
-        self._allreduce()
-        self.graph_opt.replay()
+        if self.world > 1:
+            self._allreduce()
+            self.graph_opt.replay()
+        from . import ops
+        ops.bump_weights_epoch()
         return self.out
 
 
@@ -198,6 +293,14 @@ class GraphedForward:
         with torch.cuda.graph(self.graph):
             self.out = self._run()
 
+    def _refresh_qpos(self) -> None:
+        """The captured graph reads the module's cached positional encoding; after a weight update (tracked by
+        ops.weights_epoch / torch version counters) recompute it eagerly INTO THE SAME STORAGE before replaying."""
+        ig = getattr(self.model, "infoGen", None)
+        if ig is not None and self.text is not None:
+            with torch.no_grad():
+                ig.query_pos(self.text.shape[0], self.x.shape[2], self.x.shape[3])
+
     def __call__(self, x: Optional[Tensor] = None, text_emb: Optional[Tensor] = None):
         if self.graph is None:
             self.capture()
@@ -205,5 +308,6 @@ class GraphedForward:
             self.x.copy_(x, non_blocking=True)
         if text_emb is not None:
             self.text.copy_(text_emb, non_blocking=True)
+        self._refresh_qpos()
         self.graph.replay()
         return self.out

@@ -203,10 +203,16 @@ class TPInterpreter(nn.Module):
         ps = [self.init_factor.weight] + list(gru.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in ps):
             return stages.rpe_stage(self.init_factor, gru, batch, H, W)
-        key = (batch, H, W, ps[0].device) + tuple((p.data_ptr(), p._version) for p in ps)
+        # ops.weights_epoch(): the fused clip+Adam kernel updates parameters through raw pointers (no _version bump)
+        key = (batch, H, W, ps[0].device, stages.ops.weights_epoch()) + tuple((p.data_ptr(), p._version) for p in ps)
         if self._qpos_cache is None or self._qpos_cache[0] != key:
             with torch.no_grad():
-                self._qpos_cache = (key, stages.rpe_stage(self.init_factor, gru, batch, H, W))
+                fresh = stages.rpe_stage(self.init_factor, gru, batch, H, W)
+            old = self._qpos_cache
+            if old is not None and old[0][:4] == key[:4] and old[1].shape == fresh.shape:
+                old[1].copy_(fresh)        # same storage: a CUDA graph that captured the cached tensor stays valid
+                fresh = old[1]
+            self._qpos_cache = (key, fresh)
         return self._qpos_cache[1]
 
     def forward(self, image_feature, tp_input):
@@ -335,6 +341,9 @@ class _TSRNBase(nn.Module):
         _require_cuda(x)
         if x.dim() != 4 or x.shape[1] != self._in_planes:
             raise RuntimeError("expected input [N, %d, H, W], got %s" % (self._in_planes, tuple(x.shape)))
+        if x.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("tatt_b200 does not propagate gradients into the input image (no caller of the "
+                                      "reference path needs d/dx); detach() it or keep it out of autograd")
         if self.stn and self.training:
             xw = stages.stn_tps_stage(self.stn_head, self.tps, x, True)
             return stages.stem_stage(self.block1, xw, True)

@@ -152,6 +152,40 @@ def test_eval_repeatable_and_qpos_cache():
     assert net.infoGen._qpos_cache is not cache and not torch.equal(a, c)
 
 
+def test_eval_after_trainer_step_sees_updated_weights():
+    """The fused clip+Adam kernel updates parameters through raw pointers (no torch version bump): the cached eval
+    positional encoding must still be refreshed -- eval after Trainer.step == a fresh model loaded from state_dict."""
+    import tatt_b200
+    from tatt_b200.train import GraphedForward, Trainer
+    net, sd, x, tp, cls, kw, N, training = make("tatt_g16_stn_train_n3")
+    xd, td = x.to(DEV), tp.to(DEV)
+    net.eval()
+    with torch.no_grad():
+        o0, _ = net(xd, td)                                       # fills the qpos cache with the initial weights
+    gf = GraphedForward(net, tuple(x.shape), tuple(tp.shape))
+    gf.x.copy_(xd); gf.text.copy_(td)
+    gf.capture()
+    net.train()
+    tr = Trainer(net, lr=5e-2)
+    g = torch.randn(N, 4, 32, 128, generator=torch.Generator().manual_seed(3)).to(DEV)
+    tr.step(xd, td, g)
+    net.eval()
+    with torch.no_grad():
+        o1, w1 = net(xd, td)
+    o1g, w1g = gf()
+    fresh = getattr(tatt_b200, cls)(**kw).to(DEV).eval()
+    fresh.load_state_dict(net.state_dict())
+    with torch.no_grad():
+        o2, w2 = fresh(xd, td)
+    assert not torch.equal(o0, o1)
+    assert relerr(o1, o2) <= 1e-6 and relerr(w1, w2) <= 1e-6
+    assert relerr(o1g, o2) <= 1e-6 and relerr(w1g, w2) <= 1e-6    # graph replay reads the refreshed encoding
+    # optimizer state round trip
+    st = tr.state_dict()
+    assert st["step"] == 1 and len(st["exp_avg"]) == len(tr.bucket.params)
+    tr.load_state_dict(st)
+
+
 def test_batch_position_dependence_q1():
     """Quirk Q1: the same sample replicated in a batch gets different outputs (batch-axis recurrence)."""
     net, sd, x, tp, *_ = make("tatt_g16_eval_n2")
@@ -213,11 +247,16 @@ def test_graphed_trainer_matches_eager_trainer():
     xe, te = x.to(DEV), tp.to(DEV)
     graphed = GraphedTrainer(net_g, tuple(x.shape), tuple(tp.shape), tuple(g.shape))
     graphed.x.copy_(xe); graphed.text.copy_(te); graphed.grad_out.copy_(g)
+    sd_before = {k: v.clone() for k, v in net_g.state_dict().items()}
     graphed.capture(warmup=2)
-    assert int(graphed.step_state[1].item()) == 2
+    # capture is side-effect free: warm-up steps are rolled back (weights, BN buffers, Adam state, step counter)
+    assert int(graphed.step_state[1].item()) == 0
+    for k, v in net_g.state_dict().items():
+        assert torch.equal(v, sd_before[k]), k
+    assert float(graphed.m.abs().max()) == 0.0 and float(graphed.v.abs().max()) == 0.0
     graphed.step(x.pin_memory(), tp.pin_memory())
     torch.cuda.synchronize()
-    assert int(graphed.step_state[1].item()) == 3
+    assert int(graphed.step_state[1].item()) == 1
     # same weights + BN buffers in an eager model -> gradient of the next step must match the graph replay
     net_e.load_state_dict(net_g.state_dict())
     eager = Trainer(net_e)
