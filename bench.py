@@ -27,7 +27,7 @@ import torch  # noqa: E402
 
 METRIC = "SR images/sec (32x128 LR, fwd+bwd)"
 UNIT = "images/s"
-NCU_CONV_TRAFFIC_BYTES = 182.5e6         # split pass 91.1 MB + conv3x3_roll_kernel 91.4 MB (profiles/r1d_ncu_full_conv3x3_roll.csv)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic_by_entry.json")   # written by tools/ncu_traffic.py from an ncu --set full capture
 ALG_FLOPS_FWD_BWD_G32 = 3.0 * 9.33e9     # ~9.33 GFLOP/img forward (RPE input-proj hoisted) x3 for fwd+bwd
 
 
@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--geometry", default="g32", choices=["g32", "g16"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-full-batch", type=int, default=1,
+                    help="reference arm: also time one step at the full per-GPU batch (same config as our arm)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python (no CUDA graphs)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
                     help="f32 (default, the configuration BASELINE.json's metric is quoted on: fp32 parity via "
@@ -88,96 +90,155 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_baseline(ctor_kw, h, w, sample_n, steps, warmup):
-    """The reference's own CPU path (oracle port: the same torch CPU ops in the same order), fwd+bwd,
-    dropout 0.1, all host threads."""
+def host_threads():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which made round 1's
+    N >= 2 reference lines single-threaded: the thread count is therefore set explicitly, never inherited."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, n)
+
+
+def cpu_baseline(ctor_kw, h, w, sample_n, steps, warmup, full_batch=0):
+    """The reference's own CPU path (oracle port: the same torch CPU ops in the same order): forward + backward +
+    clip_grad_norm_(0.25) + Adam(betas=(0.5, 0.999)) as interfaces/super_resolution.py:1072-1085 does, dropout 0.1, on
+    ALL host threads (set explicitly).  Steps run on a bounded `sample_n`-image batch; with full_batch > 0 one more
+    step is timed on the full per-GPU batch of our arm (same configuration) and reported as `full_batch`."""
     import tatt_b200
     from oracle import tatt_oracle as orc
+    cores = host_threads()
+    torch.set_num_threads(cores)
     torch.manual_seed(1234)
     net = tatt_b200.TSRN_TL_TRANS(**ctor_kw)          # parameter container only (CPU); never run
     sd = orc.clone_sd(net.state_dict(), requires_grad=True)
-    x, tp = orc.synthetic_inputs(sample_n, h, w, seed=1234)
-    cores = torch.get_num_threads()
-    times = []
-    for i in range(warmup + steps):
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, betas=(0.5, 0.999))
+
+    def one_step(x, tp):
         t0 = time.perf_counter()
-        for v in sd.values():
-            v.grad = None
+        opt.zero_grad(set_to_none=True)
         out, _, _ = orc.tsrn_tl_trans_forward(sd, x, tp, training=True, stn=ctor_kw["STN"], dropout_p=0.1)
         out.mean().backward()
+        torch.nn.utils.clip_grad_norm_([q for q in params if q.grad is not None], 0.25)
+        opt.step()
+        return time.perf_counter() - t0
+
+    x, tp = orc.synthetic_inputs(sample_n, h, w, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        dt = one_step(x, tp)
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
     tot = sum(times)
-    return {"value": sample_n * len(times) / tot, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d-image batch per step x %d steps of the same geometry (fwd+bwd, dropout 0.1), "
-                      "oracle port of the reference on torch CPU fp32" % (sample_n, len(times)),
-            "ms_per_step": 1e3 * tot / len(times)}
+    res = {"value": sample_n * len(times) / tot, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "%d-image batch per step x %d steps of the same geometry (fwd+bwd+clip+Adam, dropout 0.1), "
+                     "oracle port of the reference on torch CPU fp32, torch.set_num_threads(%d)" % (
+                         sample_n, len(times), cores),
+           "ms_per_step": 1e3 * tot / len(times)}
+    if full_batch and full_batch != sample_n:
+        xf, tpf = orc.synthetic_inputs(full_batch, h, w, seed=1234)
+        dt = one_step(xf, tpf)
+        res["full_batch"] = {"batch": full_batch, "value": full_batch / dt, "unit": UNIT, "ms_per_step": 1e3 * dt,
+                             "steps": 1}
+    return res
+
+
+def workload_name(kw, B):
+    return ("TSRN_TL_TRANS(width=%d,height=%d,STN=%s) fwd+bwd+clip+Adam, per-GPU batch %d, train mode dropout 0.1" % (
+        kw["width"], kw["height"], kw["STN"], B))
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port; the reference is not pip-installable,
+    DESIGN.md 5), all host threads, rank 0 only.  `value` is the throughput of the K timed steps on the bounded sample
+    batch; afterwards ONE step of the full per-GPU batch (the same configuration as our arm) is timed as well and
+    reported under config.full_batch_step / cpu_baseline.full_batch (`--ref-full-batch 0` skips it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     kw, h, w = geometry(args.geometry)
-    cb = cpu_baseline(kw, h, w, args.cpu_sample, args.steps, max(1, min(args.warmup, 2)))
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TSRN_TL_TRANS %s fwd+bwd, CPU sample batch %d" % (args.geometry, args.cpu_sample)},
-            "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    cb = cpu_baseline(kw, h, w, args.cpu_sample, args.steps, max(1, min(args.warmup, 2)),
+                      full_batch=args.batch if args.ref_full_batch else 0)
+    fb = cb.get("full_batch")
+    # value / ms_per_step stay those of the K timed sample-batch steps (so ms_per_step x steps is the real timed
+    # region); the full-batch step is extra information.  Per image the CPU path is FASTER on the small sample batch
+    # (6.3 vs ~1.3-3 img/s at batch 64), so the sample-batch figure is the conservative one for any GPU/CPU ratio.
+    value, ms = cb["value"], cb["ms_per_step"]
+    cfg = {"workload": workload_name(kw, args.cpu_sample), "per_gpu_batch": args.cpu_sample,
+           "note": "bounded sample of the %d-image workload" % args.batch}
+    if fb:
+        cfg["full_batch_step"] = fb
+    cb_line = dict(cb)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": cb_line,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def conv_roofline(dev, batch, h, w, peaks):
-    """Dominant kernel family = the 3x3 64->64 implicit-GEMM convolution on tcgen05 (11 forward instances per image
-    plus their data / weight gradients).  One "launch" = the operand split pass + conv3x3_roll_kernel of one conv, as
-    the model's forward issues it.  Algorithmic FLOPs per launch = 2 * pixels * 64 * 576 (SURVEY 8d conv figure x
-    pixels); timed alone with CUDA events on the launching stream, L2 flushed (256 MB write) between launches.
-    `kernel_only_*`: the same call with the bf16 planes already in the workspace (flag 2048: what the data-gradient
-    pass does), i.e. conv3x3_roll_kernel by itself."""
-    from tatt_b200 import _cabi, ops
-    x = torch.randn(batch, h, w, 64, device=dev)
-    wt = torch.randn(64, 64, 3, 3, device=dev) * 0.05
-    b = torch.zeros(64, device=dev)
-    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)          # 256 MiB > L2
-    ws, wsb = ops._ws(x, x.numel() + 576 * 64)
-    for _ in range(3):
-        ops.conv2d_fwd(x, wt, b, 1)
-    wtp = ops.conv_pack(wt, 64, 64, False)
-    y = torch.empty_like(x)
+def entry_cost(name, a):
+    """Algorithmic cost of one C-ABI call from its arguments: (shape key, flops, bytes, bound).  FLOPs count each MAC
+    once in fp32 terms (the bf16 hi/lo scheme spends 3 tensor-core products per MAC: that is the implementation's cost,
+    not the algorithm's); bytes = every operand read once + every result written once, fp32."""
+    f = 4.0
+    if name == "tatt_gemm":
+        M, N, K, batch = a[9], a[10], a[11], a[12]
+        return "M%d N%d K%d x%d" % (M, N, K, batch), 2.0 * M * N * K * batch, f * batch * (M * K + N * K + M * N), "tensor"
+    if name == "tatt_conv2d_igemm":
+        n, H, W, Ci, Co, KH, KW = a[4:11]
+        return ("%dx%d %d->%d" % (KH, KW, Ci, Co), 2.0 * n * H * W * Co * KH * KW * Ci,
+                f * n * H * W * (Ci + Co), "tensor")
+    if name == "tatt_conv2d_wgrad":
+        n, H, W, Ci, Co, KH, KW = a[3:10]
+        return ("%dx%d %d->%d" % (KH, KW, Ci, Co), 2.0 * n * H * W * Co * KH * KW * Ci,
+                f * n * H * W * (Ci + Co), "tensor")
+    if name == "tatt_rows_gemm":
+        M, N, KB = a[12], a[13], a[14]
+        return "K%d N%d" % (64 * KB, N), 2.0 * M * N * 64 * KB, f * M * (64 * KB + N), "hbm"
+    if name == "tatt_rows_wgrad":
+        NB, M = a[10], a[11]
+        return "NB%d" % NB, 2.0 * M * 64 * 64 * NB, f * M * 64 * (1 + NB), "hbm"
+    if name == "tatt_gru32_scan_fwd":
+        rows = a[5] * a[6]
+        return "T%d" % a[6], 2.0 * rows * 2 * 32 * 96, f * rows * (192 + 64 + 320), "hbm"
+    if name == "tatt_gru32_scan_bwd":
+        rows = a[5] * a[6]
+        return "T%d" % a[6], 2.0 * rows * 2 * 32 * 96, f * rows * (64 + 320 + 192 + 192), "hbm"
+    if name in ("tatt_rpe_fwd", "tatt_rpe_bwd"):
+        T, Wd, Hd = a[-5], a[-4], a[-3]
+        return "T%d W%d Hd%d" % (T, Wd, Hd), 2.0 * 2 * T * Wd * Hd * 3 * Hd, None, "tensor"
+    return "", None, None, "hbm"
 
-    def timed(flags):
-        ts = []
-        for _ in range(10):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _cabi.call("tatt_conv2d_igemm", x.data_ptr(), wtp.data_ptr(), b.data_ptr(), y.data_ptr(), batch, h, w, 64,
-                       64, 3, 3, 1, 1, ops._precision_flag | flags, ws.data_ptr(), wsb, ops._stream())
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e-3)
-        return sum(ts) / len(ts)
 
-    t = timed(0)
-    tk = timed(ops.F_A_VALID)
-    flops = 2.0 * batch * h * w * 64 * 576
-    peak = peaks.get("bf16_tflops", 1590.0)
-    # dram__bytes_read.sum + dram__bytes_write.sum of the split pass + conv kernel from the committed ncu --set full
-    # capture (profiles/), same shape; algorithmic bytes = 67 MB in + 67 MB out
-    traffic = NCU_CONV_TRAFFIC_BYTES if (batch, h, w) == (64, 32, 128) else None
-    bf16 = bool(ops._precision_flag & ops.F_BF16)
-    return {"bound": "tensor", "kernel": "split_dense_kernel + conv3x3_roll_kernel (conv3x3 64->64, NHWC; persistent "
-            "rolling-halo TMA tiles + TMA weight ring, tcgen05 kind::f16 with a bf16 hi/lo operand split: A_hi x [B_hi|B_lo] "
-            "(N=128) + A_lo x B_hi (N=64) per k-step, ping-pong fp32 TMEM accumulators)",
-            "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak,
-            "traffic": traffic, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if "bf16_tflops" in peaks
-            else "fallback 1.59 PFLOP/s, of fallback", "launch_ms": t * 1e3, "algorithmic_flops_per_launch": flops,
-            "kernel_only_ms": tk * 1e3, "kernel_only_tflops": flops / tk / 1e12, "kernel_only_frac": flops / tk / 1e12 / peak,
-            "note": ("bf16 mode: one MMA per product" if bf16 else
-                     "fp32-parity mode costs 3 bf16 products per MAC (ceiling = 1/3 of the bf16 peak); with C_out = 64 "
-                     "the MMAs are bound by shared-memory operand fetch, not by the tensor-pipe math rate")}
+def step_profile(trainer, Trainer, xs, ts_, third, peaks, bf16):
+    """One EAGER training step with a CUDA-event pair around every C-ABI call (tatt_b200._cabi.Profile): the launch
+    list of a step by entry point, measured live on the launching stream.  -> (top entries by share with their
+    roofline fractions, total kernel seconds).  Event pairs add ~1-2 us per call; the ncu launch list of the same
+    build under profiles/ is the cross-check."""
+    from tatt_b200 import _cabi
+    Trainer.step(trainer, xs, ts_, third)                    # warm caches / workspaces on the eager path
+    torch.cuda.synchronize()
+    with _cabi.Profile() as prof:
+        Trainer.step(trainer, xs, ts_, third)
+    rows = prof.summary(lambda n, a: (n, entry_cost(n, a)[0]))
+    total = sum(r[2] for r in rows)
+    tpk = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+    hpk = peaks.get("hbm_gbs", 6450.0)
+    top = []
+    for (n, key), calls, tsum, _, args in rows[:8]:
+        _, fl, by, bound = entry_cost(n, args)
+        avg = tsum / calls
+        e = {"entry": n, "shape": key, "calls": calls, "share": tsum / total, "avg_us": avg * 1e6, "bound": bound}
+        if fl:
+            e["tflops"] = fl / avg / 1e12
+            e["tensor_frac"] = e["tflops"] / tpk
+        if by:
+            e["gbs"] = by / avg / 1e9
+            e["hbm_frac"] = e["gbs"] / hpk
+        top.append(e)
+    return top, total, len(prof.rows)
 
 
 def run_ours(args):
@@ -193,7 +254,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     import tatt_b200
     from tatt_b200 import _cabi, ops
-    from tatt_b200.train import GraphedTrainer, Trainer
+    from tatt_b200.train import GraphedForward, GraphedTrainer, Trainer
     from oracle import tatt_oracle as orc   # only for the synthetic-input recipe and the cpu_baseline leg
 
     kw, h, w = geometry(args.geometry)
@@ -202,16 +263,18 @@ def run_ours(args):
     tatt_b200.manual_seed(1234 + rank)
     tatt_b200.set_precision("bf16" if args.dtype == "bf16" else "fp32")
     B = args.batch
+    # the step backpropagates the reference's SR loss, ImageLoss(out, hr).mean() * 100 (super_resolution.py:666;
+    # loss weights [1, 1e-4] as interfaces/base.py builds it): the third step argument is the HR target
+    lw = (1.0, 1e-4)
     if args.eager:
-        trainer = Trainer(model)
+        trainer = Trainer(model, image_loss=lw)
     else:
-        trainer = GraphedTrainer(model, (B, 4, h, w), (B, 37, 1, 26), (B, 4, 2 * h, 2 * w))
+        trainer = GraphedTrainer(model, (B, 4, h, w), (B, 37, 1, 26), (B, 4, 2 * h, 2 * w), image_loss=lw)
     x_h, tp_h = orc.synthetic_inputs(B, h, w, seed=1234 + rank)
-    x_h, tp_h = x_h.pin_memory(), tp_h.pin_memory()
-    g_h = torch.randn(B, 4, 2 * h, 2 * w, generator=torch.Generator().manual_seed(7)) / (B * 4 * 4 * h * w)
-    x_d, tp_d, g_d = x_h.to(dev), tp_h.to(dev), g_h.to(dev)
-    metric_d = torch.zeros(1, device=dev)
-    metric_h = torch.zeros(1).pin_memory()
+    hr_h = torch.rand(B, 4, 2 * h, 2 * w, generator=torch.Generator().manual_seed(7 + rank))
+    x_h, tp_h, hr_h = x_h.pin_memory(), tp_h.pin_memory(), hr_h.pin_memory()
+    x_d, tp_d, hr_d = x_h.to(dev), tp_h.to(dev), hr_h.to(dev)
+    loss_h = torch.zeros(B).pin_memory()
 
     def barrier():
         if world > 1:
@@ -221,22 +284,21 @@ def run_ours(args):
     def timed(nsteps, e2e):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = _cabi.launch_count
         e0.record()
         for _ in range(nsteps):
             if e2e and args.eager:
                 xs = x_h.to(dev, non_blocking=True)
                 ts_ = tp_h.to(dev, non_blocking=True)
+                hs = hr_h.to(dev, non_blocking=True)
             elif e2e:
-                xs, ts_ = x_h, tp_h                                # pinned host -> static device buffers
+                xs, ts_, hs = x_h, tp_h, hr_h                      # pinned host -> static device buffers
             elif args.eager:
-                xs, ts_ = x_d, tp_d
+                xs, ts_, hs = x_d, tp_d, hr_d
             else:
-                xs, ts_ = None, None                               # inputs already resident in HBM
-            out = trainer.step(xs, ts_, g_d if args.eager else None)
+                xs, ts_, hs = None, None, None                     # inputs already resident in HBM
+            trainer.step(xs, ts_, hs)
             if e2e:
-                _cabi.call("tatt_sqnorm", out.data_ptr(), out.numel(), metric_d.data_ptr(), 1, ops._stream())
-                metric_h.copy_(metric_d, non_blocking=True)
+                loss_h.copy_(trainer.loss, non_blocking=True)      # the step's result: per-sample losses -> host
                 torch.cuda.current_stream().synchronize()
         e1.record()
         barrier()
@@ -245,40 +307,52 @@ def run_ours(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
-        return ms, _cabi.launch_count - l0
+        return ms
 
     if not args.eager:
-        trainer.x.copy_(x_d); trainer.text.copy_(tp_d); trainer.grad_out.copy_(g_d)
-        l0 = _cabi.launch_count
+        trainer.x.copy_(x_d); trainer.text.copy_(tp_d); trainer.grad_out.copy_(hr_d)
         trainer.capture()
-        per_step_launches = (_cabi.launch_count - l0) // 3        # 2 eager warm-up steps + 1 captured step
     timed(max(args.warmup, 3), False)
     sampler = ClockSampler(local)
     sampler.start()
-    ms, launches = timed(args.steps, False)
+    ms = timed(args.steps, False)
     clocks = sampler.stop()
     timed(1, True)
-    ms_e2e, _ = timed(args.steps, True)
+    ms_e2e = timed(args.steps, True)
+    final_loss = float(loss_h.mean()) * 100.0
 
-    # forward-only (inference) throughput of the same model / batch, eval mode, CUDA graph, inputs resident
-    from tatt_b200.train import GraphedForward
+    # forward-only (inference): eval mode, CUDA graph; device-timed with inputs resident, and end to end through the
+    # public GraphedForward call with pinned-host inputs and the SR IMAGE copied back to the host every step
     fwd = GraphedForward(model, (B, 4, h, w), (B, 37, 1, 26))
     fwd.x.copy_(x_d); fwd.text.copy_(tp_d)
     fwd.capture()
-    for _ in range(3):
-        fwd()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        fwd()
-    f1.record()
-    barrier()
-    ms_fwd = f0.elapsed_time(f1)
-    if world > 1:
-        tf = torch.tensor([ms_fwd], device=dev)
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-        ms_fwd = tf.item()
+    sr_h = torch.empty(B, 4, 2 * h, 2 * w).pin_memory()
+
+    def timed_fwd(e2e):
+        for _ in range(3):
+            fwd()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            if e2e:
+                o, _ = fwd(x_h, tp_h)
+                sr_h.copy_(o, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            else:
+                fwd()
+        f1.record()
+        barrier()
+        t = f0.elapsed_time(f1)
+        if world > 1:
+            tf = torch.tensor([t], device=dev)
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            t = tf.item()
+        return t
+
+    ms_fwd = timed_fwd(False)
+    ms_fwd_e2e = timed_fwd(True)
+    fwd_nodes = fwd.node_counts
     model.train()
     if rank != 0:
         if world > 1:
@@ -288,26 +362,67 @@ def run_ours(args):
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
-    if not args.eager:
-        launches = per_step_launches * args.steps               # kernels replayed from the captured graphs
+    nodes = None if args.eager else trainer.node_counts           # [kernel, memcpy, memset, other] graph nodes per step
     value = B * world * args.steps / (ms * 1e-3)
     e2e_v = B * world * args.steps / (ms_e2e * 1e-3)
-    roof = conv_roofline(dev, B, h, w, peaks)
-    roof["model_algorithmic_tflops"] = value * ALG_FLOPS_FWD_BWD_G32 / 1e12 if args.geometry == "g32" else None
+
+    # ---- roofline: the time-dominant C-ABI entry of one step, measured live (eager step, CUDA events per call)
+    bf16 = args.dtype == "bf16"
+    top, ksum, ncalls = step_profile(trainer, Trainer, x_d, tp_d, hr_d, peaks, bf16)
+    traffic = {}
+    if os.path.exists(TRAFFIC_FILE):
+        traffic = json.load(open(TRAFFIC_FILE))
+    d0 = top[0]
+    tensor_bound = d0["bound"] == "tensor" and "tflops" in d0
+    tpk_burst = peaks.get("bf16_tflops", 1590.0)
+    tpk_sust = peaks.get("bf16_tflops_sustained", tpk_burst)
+    hpk = peaks.get("hbm_gbs", 6450.0)
+    alg_tflops = value / world * ALG_FLOPS_FWD_BWD_G32 / 1e12 if args.geometry == "g32" else None
+    tkey = "%s %s" % (d0["entry"], d0["shape"])
+    roof = {"bound": "tensor" if tensor_bound else "hbm",
+            "kernel": tkey + " (time-dominant C-ABI entry of one training step: %.1f %% of %.2f ms of kernel time over "
+                             "%d calls)" % (100 * d0["share"], ksum * 1e3, ncalls),
+            "achieved": d0["tflops"] if tensor_bound else d0.get("gbs"),
+            "peak": tpk_sust if tensor_bound else hpk, "unit": "TFLOP/s" if tensor_bound else "GB/s",
+            "frac": (d0["tflops"] / tpk_sust) if tensor_bound else (d0.get("gbs", 0.0) / hpk),
+            "traffic": traffic.get(tkey, {}).get("dram_bytes_per_launch"),
+            "traffic_source": traffic.get("_source"),
+            "peak_source": "MEASURED_PEAKS.json (%s; kernels timed inside a long step)" % (
+                "bf16_tflops_sustained" if tensor_bound else "hbm_gbs") if peaks else "fallback of B200_PROFILING.md",
+            "avg_launch_us": d0["avg_us"], "calls_per_step": d0["calls"],
+            "top": top,
+            "step_frac": None if alg_tflops is None else alg_tflops / tpk_sust,
+            "model_algorithmic_tflops": alg_tflops,
+            "note": ("bf16 mode: one tensor-core product per MAC" if bf16 else
+                     "fp32-parity mode spends 3 bf16 tensor-core products per algorithmic MAC (hi*hi + hi*lo + lo*hi): "
+                     "the ceiling of tensor_frac is 1/3; FLOPs are algorithmic (one MAC = 2 FLOP)")}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "TSRN_TL_TRANS(width=%d,height=%d,STN=%s) fwd+bwd+clip+Adam, per-GPU batch %d, "
-                                   "train mode dropout 0.1" % (kw["width"], kw["height"], kw["STN"], B),
+            "config": {"workload": workload_name(kw, B),
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                       "launch": "eager" if args.eager else "cuda-graphs (fwd+bwd+pack | allreduce | clip+Adam)",
-                       "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush"},
-            "clocks": clocks, "gpu_launches": launches,
+                       "loss": "ImageLoss(gradient=True, loss_weight=[1, 1e-4])(out, hr).mean() * 100 (CUDA, csrc/loss.cu)",
+                       "launch": "eager" if args.eager else "cuda-graphs (fwd+loss+bwd+pack | allreduce | clip+Adam)",
+                       "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                       "parity_note": "the timed step runs dropout 0.1 (own Philox stream); the parity-checked step is "
+                                      "the same code at p = 0 (tests/test_model_gpu.py::test_benchmarked_config_vs_golden)"},
+            "clocks": clocks,
+            "gpu_launches": (nodes[0] * args.steps) if nodes else ncalls * args.steps,
+            "graph_nodes_per_step": None if nodes is None else {"kernel": nodes[0], "memcpy": nodes[1],
+                                                                 "memset": nodes[2], "other": nodes[3]},
+            "final_loss": final_loss,
             "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": (x_h.numel() + tp_h.numel()) * 4, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": (x_h.numel() + tp_h.numel() + hr_h.numel()) * 4,
+                    "d2h_bytes_per_step": loss_h.numel() * 4},
             "forward_only": {"value": B * world * args.steps / (ms_fwd * 1e-3), "unit": UNIT,
                              "ms_per_step": ms_fwd / args.steps,
-                             "note": "eval-mode forward of the same batch, CUDA graph, cached positional encoding"},
+                             "graph_kernel_nodes": fwd_nodes[0],
+                             "e2e": {"value": B * world * args.steps / (ms_fwd_e2e * 1e-3), "unit": UNIT,
+                                     "ms_per_step": ms_fwd_e2e / args.steps,
+                                     "h2d_bytes_per_step": (x_h.numel() + tp_h.numel()) * 4,
+                                     "d2h_bytes_per_step": sr_h.numel() * 4},
+                             "note": "eval-mode forward of the same batch, CUDA graph, cached positional encoding; e2e = "
+                                     "GraphedForward(x_host, text_host) + SR image copied back to pinned host memory"},
             "roofline": roof}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(kw, h, w, args.cpu_sample, 2, 1)

@@ -23,6 +23,9 @@ const char* tatt_last_error(void);
 int tatt_version(void);
 /* 1 when the library was compiled for sm_100a (always, in this tree) */
 int tatt_arch(void);
+/* Host-only census of a captured CUDA graph (cudaGraph_t as void*): counts[4] = {kernel, memcpy, memset, other} nodes.
+ * bench.py reports counts[0] as the real number of kernel launches per replayed training step. */
+int tatt_graph_node_counts(void* graph, int* counts);
 
 /* ---- GEMM / linear layers: nn.Linear, 1x1 nn.Conv2d, GRU input/recurrent projections -------------
  * model/tsrn.py:170,1070 ; model/transformer_v2.py:453-458,785-790,177 ; model/stn_head.py:49-53

@@ -86,10 +86,57 @@ _KERNELS = {"tatt_bn_stats": 2, "tatt_bn_bwd": 3, "tatt_memcpy_d2d": 0, "tatt_me
 launch_count = 0
 
 
+_profile = None          # list of (name, args, start event, end event) while a Profile is active
+
+
+class Profile:
+    """Per-entry-point device timing of everything launched inside the `with` block: a CUDA event pair on the launching
+    (current) stream around every C-ABI call.  For eager (non-graph) steps; `summary()` groups by entry point and a
+    caller-supplied shape key.  bench.py uses it to name the time-dominant kernel of a step live."""
+
+    def __enter__(self):
+        global _profile
+        self.records = _profile = []
+        return self
+
+    def __exit__(self, *exc):
+        global _profile
+        _profile = None
+        import torch
+        torch.cuda.synchronize()
+        self.rows = [(n, a, e0.elapsed_time(e1) * 1e-3) for n, a, e0, e1 in self.records]
+        return False
+
+    def summary(self, keyfn=None):
+        """-> [(key, calls, total seconds)] sorted by total time; keyfn(name, args) -> hashable key."""
+        agg = {}
+        for n, a, t in self.rows:
+            k = keyfn(n, a) if keyfn else n
+            c = agg.setdefault(k, [0, 0.0, n, a])
+            c[0] += 1
+            c[1] += t
+        return sorted(((k, v[0], v[1], v[2], v[3]) for k, v in agg.items()), key=lambda r: -r[2])
+
+
+def call_host(name: str, *args):
+    """Entry points that launch nothing (host-side helpers)."""
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, last_error()))
+
+
 def call(name: str, *args):
     """Invoke an int-returning entry point; non-zero -> RuntimeError(tatt_last_error())."""
     global launch_count
     launch_count += _KERNELS.get(name, 1)
-    rc = getattr(lib(), name)(*args)
+    if _profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args)
+        e1.record()
+        _profile.append((name, args, e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, last_error()))

@@ -99,8 +99,16 @@ class Trainer:
     """fwd + bwd + (all-reduce) + fused clip/Adam for TSRN_TL_TRANS / TSRN on CUDA (eager launches)."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.5, 0.999), eps: float = 1e-8,
-                 max_norm: float = 0.25, group=None):
+                 max_norm: float = 0.25, group=None, image_loss: Optional[Sequence[float]] = None):
+        """image_loss = (w0, w1): the third argument of step() / forward_backward() is then the HR TARGET image and the
+        step backpropagates `ImageLoss(gradient=True, loss_weight=[w0, w1])(out, target).mean() * 100`, the reference's
+        SR loss (interfaces/super_resolution.py:666; loss/image_loss.py:10-34; base.py builds it with [1, 1e-4]), computed
+        by csrc/loss.cu (no torch ops).  `self.loss` then holds the per-sample loss vector of the last step.
+        image_loss = None: the third argument is an explicit upstream gradient d(loss)/d(out)."""
         self.model, self.lr, self.betas, self.eps, self.max_norm, self.group = model, lr, betas, eps, max_norm, group
+        self.image_loss = None if image_loss is None else (float(image_loss[0]), float(image_loss[1]))
+        self.loss: Optional[Tensor] = None
+        self._loss_ws = None
         self.bucket: Optional[GradBucket] = None
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 
@@ -109,8 +117,35 @@ class Trainer:
             p.grad = None
         res = self.model(x, text_emb) if text_emb is not None else self.model(x)
         out = res[0] if isinstance(res, tuple) else res
+        if self.image_loss is not None:
+            grad_out = self._image_loss_grad(out, grad_out)
         torch.autograd.backward([out], [grad_out])
         return out
+
+    def _image_loss_grad(self, out: Tensor, target: Tensor) -> Tensor:
+        """d/d(out) of ImageLoss(out, target).mean() * 100 through the C-ABI; keeps the per-sample losses in self.loss."""
+        from . import _cabi, ops
+        o = out.detach()
+        if not o.is_contiguous():
+            o = o.contiguous()
+        n, c, h, w = o.shape
+        if target.shape != o.shape:
+            raise RuntimeError("Trainer(image_loss=...): target %s != output %s" % (tuple(target.shape), tuple(o.shape)))
+        if self._loss_ws is None or self._loss_ws[0].shape[0] != n:
+            self._loss_ws = (torch.empty(n, dtype=torch.float32, device=o.device),
+                             torch.empty(n, 3, h, w, 2, dtype=torch.float32, device=o.device),
+                             torch.empty(2 * n, dtype=torch.float64, device=o.device),
+                             torch.full((n,), 100.0 / n, dtype=torch.float32, device=o.device))
+        loss, G, ws, gl = self._loss_ws
+        w0, w1 = self.image_loss
+        st = ops._stream()
+        _cabi.call("tatt_image_loss_fwd", o.data_ptr(), target.data_ptr(), loss.data_ptr(), G.data_ptr(), n, c, h, w,
+                   w0, w1, ws.data_ptr(), st)
+        dout = torch.empty_like(o)
+        _cabi.call("tatt_image_loss_bwd", o.data_ptr(), target.data_ptr(), G.data_ptr(), gl.data_ptr(), dout.data_ptr(),
+                   n, c, h, w, w0, w1, st)
+        self.loss = loss
+        return dout
 
     def _ensure_bucket(self) -> GradBucket:
         if self.bucket is None:
@@ -182,6 +217,15 @@ class Trainer:
         return out
 
 
+def graph_node_counts(g: "torch.cuda.CUDAGraph"):
+    """[kernel, memcpy, memset, other] node counts of a captured (keep_graph=True, not yet instantiated) CUDA graph."""
+    import ctypes
+    from . import _cabi
+    c = (ctypes.c_int * 4)()
+    _cabi.call_host("tatt_graph_node_counts", ctypes.c_void_p(int(g.raw_cuda_graph())), c)
+    return list(c)
+
+
 class GraphedTrainer(Trainer):
     """The same step captured into CUDA graphs for fixed shapes: graph 1 = forward + backward + gradient
     packing, (eager NCCL all-reduce when world > 1), graph 2 = grad-norm + clip + Adam.  Three host launches
@@ -232,16 +276,21 @@ class GraphedTrainer(Trainer):
                 Trainer.step(self, self.x, self.text, self.grad_out)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph_fb = torch.cuda.CUDAGraph()
+        self.graph_fb = torch.cuda.CUDAGraph(keep_graph=True)
         with torch.cuda.graph(self.graph_fb):
             self.out = self.forward_backward(self.x, self.text, self.grad_out)
             self._pack()
             if self.world == 1:                   # no collective in between: one graph for the whole step
                 self._update_kernels()
         if self.world > 1:
-            self.graph_opt = torch.cuda.CUDAGraph()
+            self.graph_opt = torch.cuda.CUDAGraph(keep_graph=True)
             with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
                 self._update_kernels()
+        self.node_counts = graph_node_counts(self.graph_fb)        # [kernel, memcpy, memset, other] per replayed step
+        self.graph_fb.instantiate()
+        if self.graph_opt is not None:
+            self.node_counts = [a + b for a, b in zip(self.node_counts, graph_node_counts(self.graph_opt))]
+            self.graph_opt.instantiate()
         torch.cuda.synchronize()
         self._restore(snap)                        # capture itself does not execute, but the warm-up did
 
@@ -289,9 +338,11 @@ class GraphedForward:
                 self._run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
+        self.graph = torch.cuda.CUDAGraph(keep_graph=True)
         with torch.cuda.graph(self.graph):
             self.out = self._run()
+        self.node_counts = graph_node_counts(self.graph)
+        self.graph.instantiate()
 
     def _refresh_qpos(self) -> None:
         """The captured graph reads the module's cached positional encoding; after a weight update (tracked by

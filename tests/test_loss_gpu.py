@@ -48,3 +48,37 @@ def test_image_loss_vs_oracle_large_and_odd():
         assert (od.grad.cpu().double() - ref).abs().max().item() / ref.abs().max().item() <= 1e-4
     with pytest.raises(RuntimeError):
         ImageLoss()(torch.zeros(1, 4, 4, 4), torch.zeros(1, 4, 4, 4))      # CPU tensors: no fallback path
+
+
+def test_trainer_image_loss_step_equals_autograd_loss():
+    """Trainer(image_loss=(1, 1e-4)) backpropagates ImageLoss(out, hr).mean() * 100 (interfaces/super_resolution.py:666)
+    through raw C-ABI calls: same parameter gradients as the autograd route through tatt_b200.losses.ImageLoss."""
+    import tatt_b200
+    from oracle import tatt_oracle as orc
+    from tatt_b200.losses import ImageLoss
+    from tatt_b200.train import Trainer
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    net = tatt_b200.TSRN_TL_TRANS(scale_factor=2, width=128, height=32, STN=False, mask=True).to(dev).train()
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    x, tp = orc.synthetic_inputs(3, 16, 64, seed=5)
+    hr = torch.rand(3, 4, 32, 128, generator=torch.Generator().manual_seed(6))
+    xd, td, hd = x.to(dev), tp.to(dev), hr.to(dev)
+    bn = {n: b.clone() for n, b in net.named_buffers()}
+    out, _ = net(xd, td)
+    loss = ImageLoss(gradient=True, loss_weight=[1, 1e-4])(out, hd)
+    (loss.mean() * 100).backward()
+    want = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    with torch.no_grad():
+        for n, b in net.named_buffers():
+            b.copy_(bn[n])
+    tr = Trainer(net, image_loss=(1, 1e-4))
+    tr.forward_backward(xd, td, hd)
+    assert torch.allclose(tr.loss, loss.detach(), rtol=1e-6, atol=0)
+    for n, p in net.named_parameters():
+        if n in want:
+            assert torch.equal(p.grad, want[n]), n

@@ -138,6 +138,64 @@ def test_forward_backward_vs_oracle_and_golden(case):
             gu.check_summary("buffer " + n, b.float(), fx["buffers"][n], 1e-4)
 
 
+def make_big(case):
+    import tatt_b200
+    from oracle import ref_harness as rh
+    from oracle import tatt_oracle as orc
+    cls, kw, N, training = gu.BIG_CASES[case]
+    torch.manual_seed(gu.SEED)
+    net = getattr(tatt_b200, cls)(**kw)
+    rh.zero_dropout(net)
+    rh.perturb_(net)
+    net.train(training)
+    x, tp = orc.synthetic_inputs(N, kw["height"] // 2, kw["width"] // 2, seed=gu.SEED, with_mask=kw.get("mask", True))
+    return net.to(DEV), x, tp
+
+
+def test_benchmarked_config_vs_golden():
+    """BASELINE configs[1] itself: G32, N = 64, train mode (dropout 0), forward + backward -- the batch bench.py
+    times, which selects kernel variants the small cases never reach (T = 64 batch-axis recurrence on bf16 hi/lo
+    plane hidden state, one-wave split-K GEMMs, multi-tile rolling conv, > 296 row tiles).  Checked against the
+    fixture generated from the LIVE reference (tests/golden/make_golden.py tatt_g32_train_n64; the oracle itself is
+    too slow to re-run here).  The fixture holds the reference's fp32 gradients (its float64 pass does not fit the
+    build container); at G32 without STN the reference's own fp32-vs-fp64 gradient noise is 3e-5 rel-L2.
+    Bounds: outputs / intermediates 1e-3 of max-abs; BN buffers 1e-4; per-parameter gradient norm and 64 strided
+    samples 1e-2 (+1e-5 of the model's largest gradient)."""
+    net, x, tp = make_big("tatt_g32_train_n64")
+    fx = gu.load("tatt_g32_train_n64")
+    out, aux = net(x.to(DEV), tp.to(DEV))
+    gu.check_summary("out", out, fx["out"], 1e-3)
+    for k in ("1", "4", "7"):
+        gu.check_summary("block" + k, net.block[k], fx["block" + k], 1e-3)
+    gu.check_summary("pr_weights", aux["pr_weights"], fx["pr_weights"], 1e-3)
+    gu.check_summary("tp_map", aux["spatial_t_emb"], fx["tp_map"], 1e-3)
+    errs = {}
+    for k, t in (("out", out), ("tp_map", aux["spatial_t_emb"]), ("pr_weights", aux["pr_weights"]),
+                 ("block7", net.block["7"])):
+        r = fx[k]
+        got = t.detach().double().cpu().reshape(-1)[r["idx"].long()].float()
+        errs[k] = ((got - r["val"]).abs().max() / r["val"].abs().max()).item()
+    print("N=64 G32 forward errors vs the live-reference fixture (max-abs / max-abs):", errs)
+    gen = torch.Generator().manual_seed(99)
+    wgt = torch.randn(out.shape, generator=gen)
+    (out * wgt.to(DEV)).sum().backward()
+    worst = ("", 0.0)
+    for n, p in net.named_parameters():
+        ref = fx["grads"][n]
+        if ref is None:
+            assert p.grad is None, n
+            continue
+        assert p.grad is not None, n
+        gu.check_summary("grad " + n, p.grad, ref, 1e-2, atol=1e-5 * fx["gmax"])
+        rel = abs(p.grad.double().norm().item() - ref["l2"]) / max(ref["l2"], 1e-5 * fx["gmax"])
+        if rel > worst[1]:
+            worst = (n, rel)
+    print("N=64 G32 worst per-parameter gradient-norm deviation vs the reference:", worst)
+    for n, b in net.named_buffers():
+        if "running" in n or "num_batches" in n:
+            gu.check_summary("buffer " + n, b.float(), fx["buffers"][n], 1e-4)
+
+
 def test_eval_repeatable_and_qpos_cache():
     net, sd, x, tp, cls, kw, N, training = make("tatt_g16_eval_n2")
     with torch.no_grad():
