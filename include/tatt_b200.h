@@ -131,6 +131,17 @@ int tatt_gru32_scan_bwd(const float* dOUT, const float* GATES, const float* Whh,
                         void* stream);
 
 /* ---- recurrent positional encoding (batch-axis BiGRU, quirk Q1): model/transformer_v2.py:177,215-221 -- */
+/* Persistent recurrence (tc5_rpe.cu): ONE cooperative launch runs all N steps of both directions (weight-stationary
+ * W_hh hi plane in shared memory, hidden state streamed as bf16 hi/lo planes by TMA, tcgen05 MMAs, gate math in the
+ * epilogue, per-step grid barrier).  WPL: bf16 planes of W_hh [2][3Hd][Hd] (hi, lo plane w_lo elements later);
+ * HPL: bf16 planes of HALL [2][N+1][Wd][Hd], step 0 zero, written by the kernel (lo plane h_lo elements later);
+ * sync: tatt_rpe_sync_bytes(N) bytes of scratch.  tatt_rpe_persist_supported() == 0 when shape and device qualify
+ * (Wd <= 128, Hd % 64 == 0, 2*Hd/16 CTAs co-resident); the per-step entry points below remain for other shapes. */
+int tatt_rpe_persist_supported(int N, int Wd, int Hd, int C);
+int tatt_rpe_sync_bytes(int N);
+int tatt_rpe_fwd(const float* GI, const float* BHH, const void* WPL, long long w_lo, void* HPL, long long h_lo,
+                 float* HALL, float* GATES, float* QPOS, void* sync, int N, int Wd, int Hd, int C, int Himg,
+                 void* stream);
 int tatt_rpe_gather(const float* emb, float* X, int H, int W, int C, void* stream);
 int tatt_rpe_scatter(const float* dX, float* demb, int H, int W, int C, void* stream);
 /* HPL / DGHPL: optional bf16 planes {hi, lo at +plane_lo elements} mirroring HALL / DGH (operands of the next

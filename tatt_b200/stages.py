@@ -156,6 +156,9 @@ def srb_stage(blk: torch.nn.Module, x: Tensor, tp_map: Optional[Tensor], trainin
 
 
 # ----------------------------------------------------------------------------- RPE (a7, quirk Q1)
+rpe_debug: dict = {}
+
+
 def rpe_stage(init_factor: torch.nn.Embedding, gru: torch.nn.GRU, N: int, H: int, W: int):
     """query_pos [N, H*W, 64] of InfoTransformer.forward (transformer_v2.py:201,215-221): the BiGRU
     recurs over the BATCH axis (batch_first GRU fed [W, bs, H*C]).  Its input is identical at every
@@ -199,7 +202,15 @@ def rpe_stage(init_factor: torch.nn.Embedding, gru: torch.nn.GRU, N: int, H: int
             for d in range(2):
                 WP.split_from(w_hh[d], d)
             HP = ops.Planes((2, N + 1, Wd, Hd), emb, zero=True)
-        for s in range(N):
+        persist = fast and _cabi.lib().tatt_rpe_persist_supported(N, Wd, Hd, C) == 0
+        if persist:
+            # ONE cooperative launch for all N steps of both directions (csrc/tc5_rpe.cu)
+            sync = torch.empty(_cabi.lib().tatt_rpe_sync_bytes(N) // 4, dtype=torch.int32, device=emb.device)
+            _cabi.call("tatt_rpe_fwd", GI.data_ptr(), BHH.data_ptr(), WP.t.data_ptr(), WP.lo_off, HP.t.data_ptr(),
+                       HP.lo_off, HALL.data_ptr(), None if GATES is None else GATES.data_ptr(), QPOS.data_ptr(),
+                       sync.data_ptr(), N, Wd, Hd, C, H, st())
+            rpe_debug["fwd_sync"] = sync              # sync[2N] != 0 after the run: a bounded barrier spin gave up
+        for s in range(0 if persist else N):
             if fast:
                 ops.gemm(0, 1, HP.t[0, 0, s], Hd, WP.t, Hd, GH, 3 * Hd, BHH, Wd, 3 * Hd, Hd,
                          ops.F_APLANES | ops.F_BPLANES, batch=2, sA=sH, sB=3 * Hd * Hd, sC=Wd * 3 * Hd, sBias=3 * Hd,

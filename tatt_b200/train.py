@@ -341,8 +341,12 @@ class GraphedForward:
         self.graph = torch.cuda.CUDAGraph(keep_graph=True)
         with torch.cuda.graph(self.graph):
             self.out = self._run()
+        self._ptrs = self._param_ptrs()
         self.node_counts = graph_node_counts(self.graph)
         self.graph.instantiate()
+
+    def _param_ptrs(self):
+        return [t.data_ptr() for t in list(self.model.parameters()) + list(self.model.buffers())]
 
     def _refresh_qpos(self) -> None:
         """The captured graph reads the module's cached positional encoding; after a weight update (tracked by
@@ -353,6 +357,10 @@ class GraphedForward:
                 ig.query_pos(self.text.shape[0], self.x.shape[2], self.x.shape[3])
 
     def __call__(self, x: Optional[Tensor] = None, text_emb: Optional[Tensor] = None):
+        if self.graph is not None and self._ptrs != self._param_ptrs():
+            # the graph holds raw parameter addresses: a Trainer that flattened the parameters into its bucket (or
+            # model.to() / load with assign=True) moved them -> the captured graph would read dead storage
+            self.graph = None
         if self.graph is None:
             self.capture()
         if x is not None:

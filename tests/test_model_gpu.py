@@ -186,6 +186,11 @@ def test_benchmarked_config_vs_golden():
             assert p.grad is None, n
             continue
         assert p.grad is not None, n
+        if n.endswith(("conv1.bias", "conv2.bias")) or n == "block7.0.bias":
+            # conv bias in front of a train-mode BatchNorm: the true gradient is exactly 0, both sides hold rounding
+            # noise only (the reference's own fp32 value is ~3e-5 of the model's largest gradient here)
+            assert p.grad.abs().max().item() <= 1e-4 * fx["gmax"] and ref["l2"] <= 1e-4 * fx["gmax"] * ref["n"] ** 0.5, n
+            continue
         gu.check_summary("grad " + n, p.grad, ref, 1e-2, atol=1e-5 * fx["gmax"])
         rel = abs(p.grad.double().norm().item() - ref["l2"]) / max(ref["l2"], 1e-5 * fx["gmax"])
         if rel > worst[1]:
@@ -224,7 +229,10 @@ def test_eval_after_trainer_step_sees_updated_weights():
     gf.x.copy_(xd); gf.text.copy_(td)
     gf.capture()
     net.train()
-    tr = Trainer(net, lr=5e-2)
+    # the reference's learning rate: with a huge step the scrambled network amplifies the fp32-atomics ordering noise of
+    # the split-K kernels (~1e-6) to ~1e-3, which is not what this test is about; a stale positional encoding or stale
+    # weights would still show up at ~1e-3 against the 1e-5 bound
+    tr = Trainer(net, lr=1e-3)
     g = torch.randn(N, 4, 32, 128, generator=torch.Generator().manual_seed(3)).to(DEV)
     tr.step(xd, td, g)
     net.eval()
@@ -236,8 +244,9 @@ def test_eval_after_trainer_step_sees_updated_weights():
     with torch.no_grad():
         o2, w2 = fresh(xd, td)
     assert not torch.equal(o0, o1)
-    assert relerr(o1, o2) <= 1e-6 and relerr(w1, w2) <= 1e-6
-    assert relerr(o1g, o2) <= 1e-6 and relerr(w1g, w2) <= 1e-6    # graph replay reads the refreshed encoding
+    assert relerr(o0, o1) > 1e-4                                  # the step did change the function
+    assert relerr(o1, o2) <= 1e-5 and relerr(w1, w2) <= 1e-5
+    assert relerr(o1g, o2) <= 1e-5 and relerr(w1g, w2) <= 1e-5    # graph replay reads the refreshed encoding / weights
     # optimizer state round trip
     st = tr.state_dict()
     assert st["step"] == 1 and len(st["exp_avg"]) == len(tr.bucket.params)

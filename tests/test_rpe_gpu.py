@@ -11,6 +11,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+def Wd_ok(W, H):
+    return W >= 32
+
+
 def _mk(H, W, C=64, seed=7):
     torch.manual_seed(seed)
     I = H * C
@@ -52,6 +56,8 @@ def test_rpe_long_recurrence_vs_torch_gru(N, H, W):
     embd, grud = emb.to(DEV), gru.to(DEV)
     q = stages.rpe_stage(embd, grud, N, H, W)
     assert q.shape == (N, H * W, 64)
+    if "fwd_sync" in stages.rpe_debug and Wd_ok(W, H):
+        assert int(stages.rpe_debug["fwd_sync"][2 * N].item()) == 0, "persistent RPE kernel: a step barrier timed out"
     scale = q32.abs().max().item()
     err = (q.detach().cpu() - q32.detach()).abs().max().item() / scale
     # error of the LAST step separately: rounding must not accumulate along the chain
