@@ -160,6 +160,19 @@ int tatt_mha64_bwd(const float* Q, const float* K, const float* V, const float* 
                    int N, int Lq, int Lk, float pdrop, const unsigned long long* rng, unsigned long long site,
                    void* stream);
 
+/* Fused decoder layer (tc6_declayer.cu): ONE launch = TransformerDecoderLayer_TP.forward_post + the decoder's final
+ * LayerNorm of that layer's output (model/transformer_v2.py:806-833, 380-390) for Lq %% 128 == 0 query tokens and
+ * Lk <= 32 keys per sample; every contraction (Q / out / FFN projections, per-head QK^T and PV) on tcgen05.
+ * in[18]  = tgt, query_pos [N*Lq][64]; projected K, V [N][Lk][64]; Wq, Wo, W1, W2 [64][64]; bq, bo, norm2.weight,
+ *           norm2.bias, b1, b2, norm3.weight, norm3.bias, final norm weight, bias [64].
+ * out[14] = out, inter [N*Lq][64]; head-averaged attention weights [N][Lq][Lk] or NULL; then, when train != 0, the
+ *           tensors the backward pass consumes: qin, q, a, S2, t1, h1, h1d, S3 [N*Lq][64], stats2, stats3, statsF
+ *           [2][N*Lq] (mean, rstd).  pdrop[4] / sites[4]: attention, dropout2, dropout (FFN hidden), dropout3 -- the masks
+ *           equal those of tatt_dropout / tatt_mha64_* for the same rng state and sites. */
+int tatt_tp_declayer_fwd(const float* const* in, float* const* out, int train, int N, int Lq, int Lk,
+                         const float* pdrop, const unsigned long long* rng, const unsigned long long* sites,
+                         void* stream);
+
 /* ---- element-wise / layout ------------------------------------------------------------------------------
  * PReLU (tsrn.py:598,173), PixelShuffle(2)+mish (tsrn.py:1049-1053), tanh (tsrn.py:675), Dropout,
  * MaxPool2d (stn_head.py:34-44), residual adds. */

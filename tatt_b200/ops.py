@@ -520,6 +520,29 @@ def mha_fwd(q: Tensor, k: Tensor, v: Tensor, N: int, Lq: int, Lk: int, need_weig
     return o, aw
 
 
+def declayer_ok(N: int, Lq: int, Lk: int) -> bool:
+    """the fused tcgen05 decoder-layer kernel (csrc/tc6_declayer.cu) serves this shape / precision mode"""
+    return (_declayer_enabled and not (_precision_flag & F_FP32) and Lq % 128 == 0 and 1 <= Lk <= 32)
+
+
+_declayer_enabled = os.environ.get("TATT_DECLAYER", "1") != "0"
+
+
+def declayer_fwd(ins: Sequence[Tensor], outs: Sequence[Optional[Tensor]], train: bool, N: int, Lq: int, Lk: int,
+                 pdrop: Optional[Sequence[float]], rng: Optional[Tensor], sites: Optional[Sequence[int]]) -> None:
+    """tatt_tp_declayer_fwd: ins = 18 tensors, outs = 3 (+ 11 training side outputs); see include/tatt_b200.h"""
+    import ctypes
+    assert len(ins) == 18 and len(outs) == (14 if train else 3)
+    for t in ins:
+        _chk(t, "declayer input")
+        assert t.is_contiguous()
+    pin = (ctypes.c_void_p * 18)(*[t.data_ptr() for t in ins])
+    pout = (ctypes.c_void_p * 14)(*([None if t is None else t.data_ptr() for t in outs] + [None] * (14 - len(outs))))
+    pd = (ctypes.c_float * 4)(*(pdrop if pdrop is not None else (0.0, 0.0, 0.0, 0.0)))
+    st = (ctypes.c_ulonglong * 4)(*(sites if sites is not None else (0, 0, 0, 0)))
+    _cabi.call("tatt_tp_declayer_fwd", pin, pout, 1 if train else 0, N, Lq, Lk, pd, _p(rng), st, _stream())
+
+
 def mha_bwd(q: Tensor, k: Tensor, v: Tensor, do: Tensor, N: int, Lq: int, Lk: int, pdrop: float,
             rng: Optional[Tensor], site: int):
     dq = torch.empty_like(q)

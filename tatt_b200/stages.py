@@ -326,9 +326,18 @@ def tp_stage(ig: torch.nn.Module, feat: Tensor, text_emb: Tensor, qpos: Tensor, 
         out = tgt
         inter = []
         aw = None
+        fused = ops.declayer_ok(N, H * W, L) and C == 64 and all(dd.linear1.weight.shape == (64, 64) for dd in decs)
         for i, d in enumerate(decs):
-            qin = tape.add(out, qp)
             last = i == len(decs) - 1
+            if fused:          # one tcgen05 kernel per decoder layer (csrc/tc6_declayer.cu)
+                pd = (p.get("d%da" % i, 0.0), p.get("d%d2" % i, 0.0), p.get("d%d" % i, 0.0), p.get("d%d3" % i, 0.0))
+                out, it_, w_ = tape.dec_layer(out, qp, kin, mem, d, tr.decoder.norm, N, H * W, L, last, pd, rng,
+                                              (10 + 8 * i, 11 + 8 * i, 12 + 8 * i, 13 + 8 * i))
+                inter.append(it_)
+                if last:
+                    aw = w_
+                continue
+            qin = tape.add(out, qp)
             a, w_ = tape.mha(qin, kin, mem, d.multihead_attn, N, H * W, L, last, p.get("d%da" % i, 0.0), rng,
                              10 + 8 * i)
             if last:

@@ -371,6 +371,92 @@ class Tape:
         self._push(bwd)
         return out
 
+    def _lin_bwd(self, dy: Tensor, x: Tensor, W: Tensor, want_dx: bool = True):
+        """(dW, db, dx) of y = x W^T + b for a gradient dy (row-panel kernels when the shape qualifies)"""
+        M, K = x.shape
+        N = W.shape[0]
+        if ops.rows_wgrad_ok(M, N, K) and ops.rows_gemm_ok(M, N, K):
+            dW, db = ops.linear_bwd_weight_rows(dy, x, True)
+        else:
+            dW, db = ops.linear_bwd_weight(dy, x), ops.colsum(dy)
+        return dW, db, (ops.linear_bwd_data(dy, W) if want_dx else None)
+
+    def dec_layer(self, tgt: Tensor, qp: Tensor, kin: Tensor, mem: Tensor, d: torch.nn.Module, lnf: torch.nn.Module,
+                  N: int, Lq: int, Lk: int, need_weights: bool, pd: Sequence[float], rng: Optional[Tensor],
+                  sites: Sequence[int]):
+        """TransformerDecoderLayer_TP.forward_post + the decoder's final norm of its output as ONE tcgen05 kernel
+        (csrc/tc6_declayer.cu; transformer_v2.py:806-833, 380-390).  -> (out, inter, attention weights | None).
+        pd / sites = (attention, dropout2, dropout, dropout3).  The backward pass runs the round-1 kernels on the side
+        outputs the fused forward writes (dropout masks are regenerated from the same Philox counters)."""
+        at = d.multihead_attn
+        Win, bin_ = at.in_proj_weight, at.in_proj_bias
+        Wo, bo = at.out_proj.weight, at.out_proj.bias
+        k = ops.linear_fwd(kin, Win[64:128], bin_[64:128])
+        v = ops.linear_fwd(mem, Win[128:192], bin_[128:192])
+        P = N * Lq
+        train = self.record
+        new = lambda: ops.empty(P, 64, like=tgt)
+        out, inter = new(), new()
+        aw = ops.empty(N, Lq, Lk, like=tgt) if need_weights else None
+        outs = [out, inter, aw]
+        if train:
+            qin, q, a, S2, t1, h1, h1d, S3 = (new() for _ in range(8))
+            st2, st3, stf = (ops.empty(2, P, like=tgt) for _ in range(3))
+            outs += [qin, q, a, S2, t1, h1, h1d, S3, st2, st3, stf]
+        if rng is None or not any(x > 0 for x in pd):
+            pd, rng_ = (0.0, 0.0, 0.0, 0.0), None
+        else:
+            rng_ = rng
+        ins = [tgt, qp, k, v, Win[0:64], Wo, d.linear1.weight, d.linear2.weight, bin_[0:64], bo, d.norm2.weight,
+               d.norm2.bias, d.linear1.bias, d.linear2.bias, d.norm3.weight, d.norm3.bias, lnf.weight, lnf.bias]
+        ops.declayer_fwd([t.contiguous() for t in ins], outs, train, N, Lq, Lk, pd, rng_, sites)
+
+        def bwd():
+            d_inter, d_out = self.grad(inter), self.grad(out)
+            if d_inter is None and d_out is None:
+                return
+            drop = lambda g, i: g if (rng_ is None or pd[i] <= 0.0) else ops.dropout(g, pd[i], rng_, sites[i])
+            if d_inter is not None:                               # final norm of this layer's output
+                dS, dg, db = ops.layernorm_bwd(d_inter, out, stf, lnf.weight)
+                self.add_grad(lnf.weight, dg)
+                self.add_grad(lnf.bias, db)
+                d_out = dS if d_out is None else ops.add(d_out, dS)
+            dS3, dg, db = ops.layernorm_bwd(d_out, S3, st3, d.norm3.weight)
+            self.add_grad(d.norm3.weight, dg)
+            self.add_grad(d.norm3.bias, db)
+            d_f = drop(dS3, 3)                                    # dropout3
+            dW2, db2, d_h1d = self._lin_bwd(d_f, h1d, d.linear2.weight)
+            self.add_grad(d.linear2.weight, dW2)
+            self.add_grad(d.linear2.bias, db2)
+            d_h1 = ops.relu_bwd(h1, drop(d_h1d, 2))
+            dW1, db1, d_t1 = self._lin_bwd(d_h1, t1, d.linear1.weight)
+            self.add_grad(d.linear1.weight, dW1)
+            self.add_grad(d.linear1.bias, db1)
+            d_t1 = ops.add(d_t1, dS3)
+            dS2, dg, db = ops.layernorm_bwd(d_t1, S2, st2, d.norm2.weight)
+            self.add_grad(d.norm2.weight, dg)
+            self.add_grad(d.norm2.bias, db)
+            d_y = drop(dS2, 1)                                    # dropout2
+            dWo, dbo, da = self._lin_bwd(d_y, a, Wo)
+            self.add_grad(Wo, dWo)
+            self.add_grad(bo, dbo)
+            dq, dk, dv = ops.mha_bwd(q, k, v, da, N, Lq, Lk, pd[0] if rng_ is not None else 0.0, rng_, sites[0])
+            dWin = ops.empty(192, 64, like=tgt)
+            dbin = ops.empty(192, like=tgt)
+            for i, (g, src) in enumerate(((dq, qin), (dk, kin), (dv, mem))):
+                dW_i, db_i, dx_i = self._lin_bwd(g, src, Win[i * 64:(i + 1) * 64])
+                ops.memcpy(dWin[i * 64:(i + 1) * 64], dW_i)
+                ops.memcpy(dbin[i * 64:(i + 1) * 64], db_i)
+                if i == 0:
+                    self.add_grad(tgt, ops.add(dx_i, dS2))
+                    self.add_grad(qp, dx_i)
+                else:
+                    self.add_grad(src, dx_i)
+            self.add_grad(Win, dWin)
+            self.add_grad(bin_, dbin)
+        self._push(bwd)
+        return out, inter, aw
+
     def mha(self, q_in: Tensor, k_in: Tensor, v_in: Tensor, attn: torch.nn.MultiheadAttention, N: int, Lq: int,
             Lk: int, need_weights: bool, pdrop: float, rng: Optional[Tensor], site: int):
         """nn.MultiheadAttention(64, 4) on token-major [N*L, 64] inputs -> (out [N*Lq,64], weights)."""

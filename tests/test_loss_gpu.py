@@ -79,8 +79,9 @@ def test_trainer_image_loss_step_equals_autograd_loss():
     tr = Trainer(net, image_loss=(1, 1e-4))
     tr.forward_backward(xd, td, hd)
     assert torch.allclose(tr.loss, loss.detach(), rtol=1e-6, atol=0)
+    G = max(v.abs().max().item() for v in want.values())
     for n, p in net.named_parameters():
         if n in want:
             # same kernels on both routes; split-K / partial-tile reductions use fp32 atomics, so not bit-identical
             d = (p.grad - want[n]).abs().max().item()
-            assert d <= 1e-4 * want[n].abs().max().item() + 1e-9, (n, d)
+            assert d <= 1e-4 * want[n].abs().max().item() + 1e-6 * G, (n, d)
