@@ -229,6 +229,29 @@ int tatt_image_loss_fwd(const float* out, const float* tgt, float* loss, float* 
 int tatt_image_loss_bwd(const float* out, const float* tgt, const float* G, const float* gloss, float* dout, int N, int C,
                         int H, int W, float w0, float w1, void* stream);
 
+/* ---- rest of the loss block -----------------------------------------------------------------
+ * SemanticLoss.forward, loss/semantic_loss.py:20-37: loss[0] = mean |gt - pred| + mean t (log t - log(pred + 1e-20)),
+ * t = gt + 1e-20 (nn.KLDivLoss default 'mean' reduction = over ALL n elements).  ws: >= 2 doubles.
+ * bwd: dpred / dgt (either may be NULL) = gloss[0] * d loss / d pred|gt. */
+int tatt_semantic_loss_fwd(const float* pred, const float* gt, long long n, float* loss, void* ws, void* stream);
+int tatt_semantic_loss_bwd(const float* pred, const float* gt, const float* gloss, float* dpred, float* dgt, long long n,
+                           void* stream);
+/* TRI_SSIM.forward -> _tri_ssim, utils/ssim_psnr.py:28-37,99-128,231-256: three NCHW images, depthwise 11x11 Gaussian
+ * (sigma 1.5) with zero padding, C1 = 0.01^2, C2 = 0.03^2.  per_sample 0: out[0] = mean of the ssim map (size_average);
+ * 1: out[n] = per-sample mean.  G (optional, 5*N*C*H*W floats) receives the per-pixel derivatives the backward pass
+ * blurs; ws: >= N doubles.  bwd: d1 / d2 / d3 (any may be NULL) = gout * d out / d x1|x2|x3, gout [1] or [N]. */
+int tatt_tri_ssim_fwd(const float* x1, const float* x2, const float* x3, float* out, float* G, int N, int C, int H, int W,
+                      int per_sample, void* ws, void* stream);
+int tatt_tri_ssim_bwd(const float* x1, const float* x2, const float* x3, const float* G, const float* gout, float* d1,
+                      float* d2, float* d3, int N, int C, int H, int W, int per_sample, void* stream);
+/* TextSR.torch_rotate_img, interfaces/super_resolution.py:126-157: per-sample rotation by arcs[n] with the aspect term
+ * H/W + offs[n]*2*off_range - off_range, as affine_grid + grid_sample (bilinear, zeros, align_corners=False), NCHW.
+ * bwd: dimg = adjoint (scatter) of the same sampling applied to dout (dimg is zero-filled here). */
+int tatt_rotate_img_fwd(const float* img, const float* arcs, const float* offs, float off_range, float* out, int N, int C,
+                        int H, int W, void* stream);
+int tatt_rotate_img_bwd(const float* dout, const float* arcs, const float* offs, float off_range, float* dimg, int N, int C,
+                        int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,12 +3,20 @@
 pinned to the oracle / live-reference fixtures by tests/test_model_gpu.py.  With dropout ON the two paths must still
 agree, because the fused kernel draws bit-identical masks (same Philox counters as tatt_dropout / tatt_mha64_*); this
 is the only check of the dropout-on forward that is not statistical.  Tolerance 2e-4 of max-abs (both are fp32-parity
-tensor-core paths; accumulation order differs), gradients 1e-3 rel-L2 per parameter."""
+tensor-core paths; accumulation order differs).  Gradients: 5e-3 rel-L2 per parameter and 1e-3 over the whole gradient.
+The per-parameter bound is what the FFN's ReLU allows, not what the GEMMs deliver: two forward passes that agree to 3e-5
+still disagree on the sign of a handful of the N*Lq*64 pre-activations, and every flipped mask element moves the
+gradients upstream of that ReLU by a full element -- measured against the fp64 oracle (tools/diag_declayer.py, G16, N = 3)
+BOTH paths sit at 0.5-2e-3 on exactly those parameters (decoder layer 0 from linear1 upstream, encoder, fc_in, RPE) and
+at 2-4e-5 everywhere else, while they agree with each other to 2e-5 downstream of the flips."""
 import pytest
 import torch
 
+import re
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+_ZERO_GRAD = re.compile(r"^(block[2-6]\.conv[12]\.bias|block7\.0\.bias)$")
 
 
 def _run(fused, kw, N, p_drop, seed=77):
@@ -22,7 +30,7 @@ def _run(fused, kw, N, p_drop, seed=77):
     if p_drop == 0.0:
         rh.zero_dropout(net)
     net = net.to(DEV).train()
-    x, tp = orc.synthetic_inputs(N, kw["height"] // 2, kw["width"] // 2, seed=5)
+    x, tp = orc.synthetic_inputs(N, kw["height"] // 2, kw["width"] // 2, seed=5, with_mask=kw["mask"])
     tatt_b200.manual_seed(seed)
     old = ops._declayer_enabled
     ops._declayer_enabled = fused
@@ -49,10 +57,23 @@ def test_fused_decoder_layer_equals_op_by_op_path(geom, N, p_drop):
     assert (a[1].sum(-1).mean() - 1).abs().item() < (1e-4 if p_drop == 0 else 2e-2)
     assert set(a[3]) == set(b[3])
     G = max(v.abs().max().item() for v in b[3].values())
+    bad = []
+    num2 = den2 = 0.0
     for n in b[3]:
         d = (a[3][n] - b[3][n]).double()
+        num2 += d.pow(2).sum().item()
+        den2 += b[3][n].double().pow(2).sum().item()
+        if _ZERO_GRAD.match(n):
+            # a conv bias in front of a train-mode BatchNorm has an exactly-zero gradient: what either path holds is
+            # summation noise (1e-7 of the sibling weight gradient), not a quantity two paths can agree on
+            assert a[3][n].abs().max().item() <= 1e-4 * G, n
+            continue
         rel = d.norm().item() / max(b[3][n].double().norm().item(), 1e-6 * G * d.numel() ** 0.5)
-        assert rel <= 1e-3, "grad %s: fused vs op-by-op rel-L2 %.3e" % (n, rel)
+        # a 1-element parameter (the PReLU slope) is one heavily cancelling sum over all tokens: 2e-2
+        if rel > (5e-3 if d.numel() > 1 else 2e-2):
+            bad.append("%s %.3e" % (n, rel))
+    assert not bad, "fused vs op-by-op gradient rel-L2 > 5e-3: " + ", ".join(bad)
+    assert (num2 / den2) ** 0.5 <= 1e-3
 
 
 def test_fused_decoder_layer_eval_matches_op_by_op():
