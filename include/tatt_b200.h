@@ -252,6 +252,36 @@ int tatt_rotate_img_fwd(const float* img, const float* arcs, const float* offs, 
 int tatt_rotate_img_bwd(const float* dout, const float* arcs, const float* offs, float off_range, float* dimg, int N, int C,
                         int H, int W, void* stream);
 
+/* ---- CRNN text-prior generator in front of the path: model/crnn/crnn.py:5-93 ----------------------
+ * Its convolutions / BatchNorm+ReLU / linear layers / per-step recurrent GEMMs use tatt_conv2d_*, tatt_bn_*, tatt_gemm.
+ * parse_crnn_data (interfaces/base.py:797-815): NCHW image (C >= 3) -> bicubic resize (torch upsample_bicubic2d,
+ * align_corners=False, A = -0.75) -> 0.299 R + 0.587 G + 0.114 B, out [N][OH][OW]. */
+int tatt_bicubic_gray(const float* img, float* out, int N, int C, int H, int W, int OH, int OW, void* stream);
+/* nn.MaxPool2d(kernel, stride, padding) on NHWC maps, floor mode (crnn.py:56-66; the (2,2),(2,1),(0,1) windows overlap).
+ * bwd: din = gradient routed to each window's first arg-max (torch's tie rule); gather form, no atomics. */
+int tatt_maxpool2d_fwd(const float* in, float* out, long long N, int H, int W, int C, int kh, int kw, int sh, int sw, int ph,
+                       int pw, void* stream);
+int tatt_maxpool2d_bwd(const float* in, const float* dout, float* din, long long N, int H, int W, int C, int kh, int kw,
+                       int sh, int sw, int ph, int pw, void* stream);
+/* pad 0: out [N][OH][OW][C] = top-left crop of in [N][H][W][C]; pad 1: out [N][H][W][C] = in [N][OH][OW][C] zero-padded
+ * (conv6 of crnn.py:68 is a 2x2 convolution without padding: same-size convolution + crop) */
+int tatt_crop_nhwc(const float* in, float* out, long long N, int H, int W, int OH, int OW, int C, int pad, void* stream);
+/* [A][B][C] -> [B][A][C] (crnn.py:85-86 permute(2, 0, 1) of the squeezed feature map; logits back to [T, N, C]) */
+int tatt_permute_102(const float* in, float* out, int A, int B, int C, void* stream);
+/* One time step of nn.LSTM(bidirectional=True) (crnn.py:9,19), both directions: step s handles time s (forward) and
+ * T-1-s (reverse).  G [T*Nb][8H]: rows t*Nb+n, columns [dir][i f g o][H]; W_ih x + b_ih on entry, activated gates on exit.
+ * GH [2][Nb][4H] = W_hh h_prev + b_hh (NULL at s == 0: BHH [2][4H] is used), CS [2][T][Nb][H] cell states,
+ * OUT [T*Nb][2H] = [h_fwd | h_bwd].  bwd (steps T-1 .. 0): dG = pre-activation gate gradients of this step's rows,
+ * DH [2][Nb][H] = recurrent hidden gradient (ignored at s == T-1), DC [2][Nb][H] cell gradient (in/out). */
+int tatt_lstm_gate_fwd(float* G, const float* GH, const float* BHH, float* CS, float* OUT, int s, int T, int Nb, int H,
+                       void* stream);
+int tatt_lstm_gate_bwd(const float* G, const float* CS, const float* dOUT, const float* DH, float* DC, float* dG, int s,
+                       int T, int Nb, int H, void* stream);
+/* interfaces/super_resolution.py:796-799: probs [T*Nb][C] = softmax over the C <= 64 classes of logits [T][Nb][C];
+ * prior (optional) [Nb][C][1][T] = the permuted text prior the SR model consumes.  bwd: dlogits from dprobs. */
+int tatt_softmax_prior_fwd(const float* logits, float* probs, float* prior, int T, int Nb, int C, void* stream);
+int tatt_softmax_bwd(const float* probs, const float* dprobs, float* dlogits, long long R, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -343,9 +343,11 @@ def _conv_ws(x: Tensor, nx: int, ndy: int, extra: int):
     return torch.empty(nbytes, dtype=torch.uint8, device=x.device)
 
 
-def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Optional[dict] = None) -> Tensor:
-    """x [N,H,W,CinP] (CinP >= w.shape[1], multiple of 4) -> y [N,H,W,CoutP].  `keep` (a dict owned by the caller's
-    tape entry) receives the workspace whose X planes the backward pass reuses."""
+def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Optional[dict] = None,
+               relu: bool = False) -> Tensor:
+    """x [N,H,W,CinP] (CinP >= w.shape[1], multiple of 4) -> y [N,H,W,CoutP] (same H x W: out-of-image taps read 0).
+    `keep` (a dict owned by the caller's tape entry) receives the workspace whose X planes the backward pass reuses;
+    `relu` fuses max(., 0) into the epilogue (generic engine only)."""
     n, h, wd, cin_p = x.shape
     co, ci, kh, kw = w.shape
     cout_p = _pad4(co)
@@ -355,7 +357,7 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Option
         b = bp
     y = empty(n, h, wd, cout_p, like=x)
     P = n * h * wd
-    if cout_p == 4 and kw > 1 and cin_p >= 16:
+    if cout_p == 4 and kw > 1 and cin_p >= 16 and not relu:
         # kx-expansion (see gemm.cu): vertical-tap GEMM with N = kw*4, then a horizontal shift-sum
         wte = empty(kh * cin_p, kw * 4, like=x)
         _cabi.call("tatt_conv_kxexp_pack", _p(w.contiguous()), _p(wte), co, ci, kh, kw, cin_p, 4, _stream())
@@ -371,7 +373,7 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Option
     ws = _conv_ws(x, x.numel(), P * _r8(cout_p),
                   max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
     _cabi.call("tatt_conv2d_igemm", _p(x), _p(wt), _p(b), _p(y), n, h, wd, cin_p, cout_p, kh, kw, pad, pad,
-               _precision_flag, _p(ws), 0 if ws is None else ws.numel(), _stream())
+               _precision_flag | (F_RELU if relu else 0), _p(ws), 0 if ws is None else ws.numel(), _stream())
     if keep is not None:
         keep["ws"] = ws
     return y

@@ -134,14 +134,17 @@ class Tape:
         self._push(bwd)
         return y
 
-    def conv(self, x4: Tensor, w: Tensor, b: Optional[Tensor], pad: int, need_dx: bool = True) -> Tensor:
+    def conv(self, x4: Tensor, w: Tensor, b: Optional[Tensor], pad: int, need_dx: bool = True,
+             relu: bool = False) -> Tensor:
         keep = {} if self.record else None       # workspace whose X planes the backward pass reuses
-        y = ops.conv2d_fwd(x4, w, b, pad, keep=keep)
+        y = ops.conv2d_fwd(x4, w, b, pad, keep=keep, relu=relu)
 
         def bwd():
             dy = self.grad(y)
             if dy is None:
                 return
+            if relu:
+                dy = ops.relu_bwd(y, dy)
             dx, dw, db = ops.conv2d_bwd(x4, w, dy, pad, need_dx=need_dx, has_bias=b is not None, keep=keep)
             self.add_grad(w, dw)
             if b is not None:

@@ -1,0 +1,176 @@
+"""Parity of the CUDA CRNN text-prior generator (tatt_b200/crnn.py + csrc/crnn.cu) against the fixture
+generated from the LIVE reference `model/crnn/crnn.py:CRNN(32, 1, 37, 256)` (tests/golden/make_golden_crnn.py) and
+against the CPU oracle (oracle/crnn_oracle.py, itself bit-exact vs the live class).  Tolerances: pre-processing 1e-5;
+logits 1e-3 of max-abs (measured 3e-5); BatchNorm running statistics 1e-4.
+Gradients vs the fp64 oracle: everything downstream of the last ReLU / max-pool (conv6, batchnorm6, both BiLSTMs and
+their embeddings) 1e-3 rel-L2 per parameter (measured 4e-5..8e-5) -- that is the smooth part, where the bound tests the
+kernels.  The 6 convolution blocks below it are piecewise linear: a forward pass that is accurate to 3e-5 decides a
+handful of the ~10^5 ReLU signs / pooling arg-maxes per layer differently, and every flipped decision moves ALL upstream
+gradients by ~1/sqrt(#active elements) (measured with tools/diag_crnn.py: 3e-3 at conv5 growing to 2e-2 at conv0 in the
+tensor-core mode, 8e-4..1e-3 on the fp32 FFMA kernels whose forward error is 3e-6, 2e-6 for torch CPU fp32).  So the
+CNN part is bounded at 6e-2 in the default mode and at 5e-3 with the same code on the FFMA kernels (`set_precision('ffma')`)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+SEED = 1234
+
+
+def _fixture():
+    return torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "crnn_n3.pt"), weights_only=False)
+
+
+def _inputs(n=3, seed=SEED, h=16, w=64):
+    return torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(seed))
+
+
+def _build(training):
+    from oracle import crnn_oracle as co
+    from tatt_b200.crnn import CRNN
+    torch.manual_seed(SEED)
+    net = CRNN(32, 1, 37, 256)
+    co.perturb_bn_(net.state_dict(), SEED + 1)
+    return net.train(training)
+
+
+def test_parse_crnn_data_bicubic_gray():
+    from oracle import crnn_oracle as co
+    from tatt_b200.crnn import parse_crnn_data
+    fx = _fixture()
+    got = parse_crnn_data(_inputs().to(DEV))
+    assert got.shape == fx["gray"].shape == (3, 1, 32, 100)
+    assert (got.cpu() - fx["gray"]).abs().max().item() <= 1e-5
+    for shape in ((2, 4, 32, 128), (1, 3, 64, 256), (2, 3, 7, 9)):      # identity height, down-scaling, tiny (clamped taps)
+        x = torch.rand(*shape, generator=torch.Generator().manual_seed(3))
+        assert (parse_crnn_data(x.to(DEV)).cpu() - co.parse_crnn_data(x[:, :3])).abs().max().item() <= 1e-5
+    with pytest.raises(RuntimeError):
+        parse_crnn_data(_inputs())                                      # CPU tensor: no fallback
+
+
+def test_crnn_eval_and_train_vs_reference_fixture_and_oracle():
+    from oracle import crnn_oracle as co
+    from tatt_b200.crnn import parse_crnn_data
+    fx = _fixture()
+    gray = parse_crnn_data(_inputs().to(DEV))
+    net = _build(False).to(DEV)
+    with torch.no_grad():
+        logits = net(gray)
+    assert logits.shape == fx["eval_logits"].shape == (26, 3, 37)
+    scale = fx["eval_logits"].abs().max().item()
+    assert (logits.cpu() - fx["eval_logits"]).abs().max().item() <= 1e-3 * scale
+
+    net = _build(True)
+    sd64 = {k: (v.detach().double() if v.is_floating_point() else v.detach().clone()) for k, v in net.state_dict().items()}
+    for k, v in sd64.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    net = net.to(DEV)
+    logits = net(gray)
+    assert (logits.detach().cpu() - fx["train_logits"]).abs().max().item() <= 1e-3 * fx["train_logits"].abs().max().item()
+    wgt = torch.randn(logits.shape, generator=torch.Generator().manual_seed(99))
+    (logits * wgt.to(DEV)).sum().backward()
+    g_cpu = gray.cpu()
+    (co.crnn_forward(sd64, g_cpu.double(), training=True) * wgt.double()).sum().backward()
+    G = max(v.grad.abs().max().item() for v in sd64.values() if v.requires_grad)
+
+    def check(grads, tol_cnn, tag):
+        bad = []
+        for n, g in grads.items():
+            og = sd64[n].grad
+            if n in ("cnn.conv2.bias", "cnn.conv4.bias", "cnn.conv6.bias"):
+                assert g.abs().max().item() <= 1e-4 * G, n          # exactly-zero gradient (train-mode BatchNorm follows)
+                continue
+            smooth = n.startswith("rnn.") or n.startswith("cnn.conv6") or n.startswith("cnn.batchnorm6")
+            rel = (g.double().cpu() - og).norm().item() / max(og.norm().item(), 1e-6 * G * og.numel() ** 0.5)
+            if rel > (1e-3 if smooth else tol_cnn):
+                bad.append("%s %.2e" % (n, rel))
+        assert not bad, "%s: gradient rel-L2 vs fp64 oracle out of bounds: %s" % (tag, ", ".join(bad))
+
+    grads = {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+    check(grads, 6e-2, "tensor-core fp32-parity mode")
+    for n, p in net.named_parameters():                              # samples of the live reference's fp32 gradient
+        ref = fx["train_grads"][n]
+        if n in ("cnn.conv2.bias", "cnn.conv4.bias", "cnn.conv6.bias"):
+            continue
+        got = p.grad.detach().cpu().reshape(-1)[ref["idx"]]
+        smooth = n.startswith("rnn.") or n.startswith("cnn.conv6") or n.startswith("cnn.batchnorm6")
+        rel = (got - ref["val"]).norm().item() / max(ref["val"].norm().item(), 1e-6 * G * got.numel() ** 0.5)
+        assert rel <= (1e-3 if smooth else 6e-2), "%s: sampled gradient vs live-reference fixture rel-L2 %.2e" % (n, rel)
+    from tatt_b200 import ops
+    bufs = {n: b.detach().clone() for n, b in net.named_buffers()}
+    ops.set_precision("ffma")
+    try:
+        net.zero_grad(set_to_none=True)
+        (net(gray) * wgt.to(DEV)).sum().backward()
+    finally:
+        ops.set_precision("fp32")
+    check({n: p.grad.detach().clone() for n, p in net.named_parameters()}, 5e-3, "fp32 FFMA kernels")
+    with torch.no_grad():
+        for n, b in net.named_buffers():
+            b.copy_(bufs[n])
+    for n, b in net.named_buffers():
+        ref = fx["train_buffers"][n]
+        if ref.is_floating_point():
+            assert (b.cpu() - ref).abs().max().item() <= 1e-4 * max(ref.abs().max().item(), 1.0), n
+        else:
+            assert int(b.item()) == int(ref.item()), n
+
+
+def test_softmax_prior_and_end_to_end_prior_into_sr_model():
+    """logits -> (label_vecs [T,N,C], prior [N,C,1,T]) like super_resolution.py:796-799; the gradient of a loss on
+    label_vecs reaches the CRNN parameters; the prior feeds TSRN_TL_TRANS directly (LR image in -> SR image out)."""
+    import tatt_b200
+    from oracle import crnn_oracle as co
+    from tatt_b200.crnn import parse_crnn_data, softmax_prior
+    from tatt_b200.losses import SemanticLoss
+    g = torch.Generator().manual_seed(5)
+    lg = torch.randn(26, 4, 37, generator=g)
+    lv, prior = softmax_prior(lg.to(DEV).requires_grad_(True))
+    assert prior.shape == (4, 37, 1, 26) and not prior.requires_grad
+    assert (prior.cpu() - co.text_prior(lg)).abs().max().item() <= 1e-6
+    l64 = lg.double().requires_grad_(True)
+    w = torch.randn(26, 4, 37, generator=g)
+    (torch.softmax(l64, -1) * w.double()).sum().backward()
+    lgd = lg.to(DEV).requires_grad_(True)
+    (softmax_prior(lgd)[0] * w.to(DEV)).sum().backward()
+    assert (lgd.grad.cpu().double() - l64.grad).abs().max().item() <= 1e-6
+
+    net = _build(True).to(DEV)
+    lr = torch.rand(4, 4, 16, 64, generator=g).to(DEV)
+    logits = net(parse_crnn_data(lr[:, :3]))
+    label_vecs, prior = softmax_prior(logits)
+    teacher = torch.softmax(torch.randn(26, 4, 37, generator=g), -1).to(DEV)
+    (SemanticLoss()(label_vecs, teacher) * 100).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    torch.manual_seed(0)
+    sr = tatt_b200.TSRN_TL_TRANS(scale_factor=2, width=128, height=32, STN=False, mask=True).to(DEV).eval()
+    with torch.no_grad():
+        out, _ = sr(lr, prior)
+    assert out.shape == (4, 4, 32, 128) and torch.isfinite(out).all()
+
+
+def test_maxpool2d_overlapping_windows_vs_torch():
+    """the CRNN's (2,2)/(2,1)/(0,1) pooling: values bit-exact, gradient routing (ties -> first maximum) like torch"""
+    from tatt_b200 import _cabi, ops
+    g = torch.Generator().manual_seed(8)
+    x = torch.relu(torch.randn(3, 16, 8, 25, generator=g))           # NCHW, many exact-zero ties
+    x[0, :, 2:4, 3:6] = 0.7                                            # a plateau: ties between equal positive values
+    for k, s, p in (((2, 2), (2, 1), (0, 1)), ((2, 2), (2, 2), (0, 0)), ((3, 2), (1, 2), (1, 1))):
+        xr = x.clone().requires_grad_(True)
+        y = torch.nn.functional.max_pool2d(xr, k, s, p)
+        w = torch.randn(y.shape, generator=g)
+        (y * w).sum().backward()
+        x4 = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+        n, h, wd, c = x4.shape
+        oh, ow = y.shape[2], y.shape[3]
+        out = torch.empty(n, oh, ow, c, device=DEV)
+        args = (n, h, wd, c, k[0], k[1], s[0], s[1], p[0], p[1])
+        _cabi.call("tatt_maxpool2d_fwd", x4.data_ptr(), out.data_ptr(), *args, ops._stream())
+        assert torch.equal(out.permute(0, 3, 1, 2).cpu(), y.detach())
+        dx = torch.empty_like(x4)
+        dy = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+        _cabi.call("tatt_maxpool2d_bwd", x4.data_ptr(), dy.data_ptr(), dx.data_ptr(), *args, ops._stream())
+        assert (dx.permute(0, 3, 1, 2).cpu() - xr.grad).abs().max().item() <= 1e-6

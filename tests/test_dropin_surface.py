@@ -115,3 +115,42 @@ def test_image_loss_surface_cpu():
         ImageLoss(gradient=False)(x, x)
     with pytest.raises(RuntimeError, match="CUDA"):
         ImageLoss()(x, x)
+
+
+def test_crnn_surface_and_fresh_init():
+    """`tatt_b200.crnn.CRNN` mirrors `model/crnn/crnn.py:CRNN`: constructor, state_dict keys / shapes and bit-identical
+    fresh initialisation (same torch.nn leaves in the same order) -- against the reference-free factory of the oracle and,
+    in the build container, against the live class; leaves are containers; CPU tensors raise (no fallback)."""
+    import pytest
+    import torch
+    from oracle import crnn_oracle as co
+    from oracle import ref_harness as rh
+    from tatt_b200.crnn import CRNN
+    torch.manual_seed(77)
+    net = CRNN(32, 1, 37, 256)
+    sd = net.state_dict()
+    want = co.make_state_dict(77)
+    assert list(sd.keys()) == list(want.keys())
+    for k in want:
+        assert torch.equal(sd[k], want[k]), k
+    if rh.available():
+        import importlib
+        import warnings
+        rh.load()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = importlib.import_module("model.crnn.crnn")
+        torch.manual_seed(77)
+        ref = mod.CRNN(32, 1, 37, 256)
+        rsd = ref.state_dict()
+        assert list(rsd.keys()) == list(sd.keys())
+        assert all(torch.equal(rsd[k], sd[k]) for k in sd)
+        ref.load_state_dict(sd, strict=True)
+        net.load_state_dict(rsd, strict=True)
+        assert [n for n, _ in ref.named_modules()] == [n for n, _ in net.named_modules()]
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(2, 1, 32, 100))
+    with pytest.raises(RuntimeError):
+        net.rnn[0](torch.zeros(26, 2, 512))
+    with pytest.raises(NotImplementedError):
+        CRNN(32, 1, 37, 256, leakyRelu=True)
