@@ -282,6 +282,11 @@ int tatt_lstm_gate_bwd(const float* G, const float* CS, const float* dOUT, const
 int tatt_softmax_prior_fwd(const float* logits, float* probs, float* prior, int T, int Nb, int C, void* stream);
 int tatt_softmax_bwd(const float* probs, const float* dprobs, float* dlogits, long long R, int C, void* stream);
 
+/* ---- TextZoom collate, device half: dataset/dataset.py:1266-1319 (resizeNormalize after the PIL resize) --
+ * img: uint8 [N][H][W][3] (RGB, HWC) -> out fp32 [N][3 + with_mask][H][W] = ToTensor() (x / 255) and, with_mask != 0, the
+ * mean-threshold mask channel (1 where PIL luma L <= mean(L), else 0).  Bit-exact integer / IEEE arithmetic. */
+int tatt_collate_u8(const void* img, float* out, int N, int H, int W, int with_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
