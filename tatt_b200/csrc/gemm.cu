@@ -706,10 +706,10 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
                       void* stream) {
   TATT_REQUIRE(Cin % 4 == 0, "conv2d_igemm: Cin (%d) must be a multiple of 4 (pad channels)", Cin);
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv2d_igemm: too many pixels");
-  if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout == 64 && ws &&
+  if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout % 64 == 0 && Cout <= 256 && ws &&
       !(flags & (F_ACCUM | F_RELU | F_FP32))) {
-    int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws, ws_bytes,
-                                     (cudaStream_t)stream);
+    int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, Cout, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
+                                     ws_bytes, (cudaStream_t)stream);
     if (rc >= 0) return rc;
   }
   GemmP p = {};
@@ -733,9 +733,10 @@ int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv2d_wgrad: too many pixels");
   cudaStream_t st = (cudaStream_t)stream;
   TATT_CUDA(cudaMemsetAsync(dWt, 0, sizeof(float) * (size_t)KH * KW * Cin * Cout, st));
-  if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout == 64 && ws && !(flags & F_FP32)) {
-    int rc = tatt_tc3_conv3x3_wgrad_launch(X, dY, dWt, nimg, H, W, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
-                                           ws_bytes, st);
+  if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout % 64 == 0 && Cout <= 256 && ws &&
+      !(flags & F_FP32)) {
+    int rc = tatt_tc3_conv3x3_wgrad_launch(X, dY, dWt, nimg, H, W, Cout, (flags & F_BF16) ? 1 : 0,
+                                           (flags & F_A_VALID) ? 1 : 0, ws, ws_bytes, st);
     if (rc >= 0) return rc;
   }
   GemmP p = {};

@@ -291,7 +291,10 @@ template <bool single, bool cat>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                    float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles, int dbg) {
+                    float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles, int dbg, int ldy,
+                    int ngroups) {
+  // C_out = 64 * ngroups: work item w = g * ntiles + t is the 64-channel output group g of pixel tile t (the same halo
+  // tile is re-read per group, mostly from L2; every group is the 64 -> 64 problem with its own weight slice)
   constexpr uint32_t acc_stride = cat ? 256u : 128u, row_stride = cat ? 128u : 64u;
   constexpr uint32_t tmem_cols = cat ? 512u : 256u;
   extern __shared__ unsigned char smem_raw[];
@@ -301,8 +304,8 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nyb = H / 2, nxt = W / TW;
-  const int t0 = (int)((long long)blockIdx.x * ntiles / gridDim.x);
-  const int t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
+  const int t0 = (int)((long long)blockIdx.x * ntiles * ngroups / gridDim.x);
+  const int t1 = (int)((long long)(blockIdx.x + 1) * ntiles * ngroups / gridDim.x);
   const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + RL_A_PLANE, b_ring = a_lo + RL_A_PLANE;
   unsigned char* stg_base = smem + 2 * RL_A_PLANE + RL_NSTAGE * B_TAP_BYTES;
 
@@ -343,10 +346,11 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       int ws = 0;                                 // weight ring stage
       uint32_t wpar = 0;                          // parity of the NEXT wait on w_empty[ws] (valid once the ring wrapped)
       bool wrapped = false;
-      for (int t = t0; t < t1; ++t) {
+      for (int w = t0; w < t1; ++w) {
+        const int g = w / ntiles, t = w - g * ntiles;
         const int yb = t % nyb, xb = (t / nyb) % nxt, n = t / (nyb * nxt);
         const int y0 = 2 * yb, x0 = xb * TW;
-        const bool fresh = (t == t0) || (yb == 0);
+        const bool fresh = (w == t0) || (yb == 0);
         const int p0 = (y0 >> 1) & 1;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -362,12 +366,12 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           if (pr) ++nload1; else ++nload0;
         }
         for (int tap = 0; tap < 9; ++tap) {
-          if ((dbg & 2) && (t > t0 || tap >= RL_NSTAGE)) break;
+          if ((dbg & 2) && (w > t0 || tap >= RL_NSTAGE)) break;
           if (wrapped) mbar_wait(smem_u32(&w_empty[ws]), wpar);
           const uint32_t dst = b_ring + (uint32_t)(ws * B_TAP_BYTES);
           mbar_expect_tx(smem_u32(&w_full[ws]), (uint32_t)(single ? B_TAP_BYTES / 2 : B_TAP_BYTES));
-          tma_load_2d(dst, &tmBh, smem_u32(&w_full[ws]), tap * 64, 0);
-          if (!single) tma_load_2d(dst + 64 * 128, &tmBl, smem_u32(&w_full[ws]), tap * 64, 0);
+          tma_load_2d(dst, &tmBh, smem_u32(&w_full[ws]), tap * 64, g * 64);
+          if (!single) tma_load_2d(dst + 64 * 128, &tmBl, smem_u32(&w_full[ws]), tap * 64, g * 64);
           if (++ws == RL_NSTAGE) {
             ws = 0;
             if (wrapped) wpar ^= 1;
@@ -386,11 +390,12 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       int ws = 0;
       uint32_t wpar = 0;
       int it = 0;
-      for (int t = t0; t < t1; ++t, ++it) {
+      for (int w = t0; w < t1; ++w, ++it) {
+        const int t = w % ntiles;
         const int yb = t % nyb;
         const int y0 = 2 * yb;
-        const bool fresh = (t == t0) || (yb == 0);
-        const bool next_fresh = (t + 1 < t1) && (((t + 1) % nyb) == 0);
+        const bool fresh = (w == t0) || (yb == 0);
+        const bool next_fresh = (w + 1 < t1) && (((t + 1) % nyb) == 0);
         const int p0 = (y0 >> 1) & 1, p1 = p0 ^ 1;
         if (it >= 2) mbar_wait(smem_u32(&acc_empty[it & 1]), (uint32_t)(((it >> 1) - 1) & 1));
         if (fresh) {
@@ -414,7 +419,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             mbar_wait(smem_u32(&pair_full[p1]), (uint32_t)((p1 ? nfull1 : nfull0) & 1));
             if (p1) ++nfull1; else ++nfull0;
           }
-          if (!((dbg & 2) && (t > t0 || tap >= RL_NSTAGE))) mbar_wait(smem_u32(&w_full[ws]), wpar);
+          if (!((dbg & 2) && (w > t0 || tap >= RL_NSTAGE))) mbar_wait(smem_u32(&w_full[ws]), wpar);
           tc_fence_after();
           const uint32_t bh = ((b_ring + (uint32_t)(ws * B_TAP_BYTES)) >> 4) | LBO1, bl = bh + ((64 * 128) >> 4);
           // per output row: lo*hi, hi*lo, hi*hi back to back (consecutive MMAs that share an operand are cheaper: the
@@ -457,19 +462,24 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     const int lg = warp & 3;
     unsigned char* stg = stg_base + lg * (32 * 128);
     const int pq = lane >> 3, cc = lane & 7;          // copy-out: pixel 4 i + pq, float4 column cc of the 32-channel half
-    float4 bb[2];
+    float4 bb[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    int it = 0, gcur = -1;
+    for (int w = t0; w < t1; ++w, ++it) {
+      const int g = w / ntiles, t = w - g * ntiles;
+      if (g != gcur) {
+        gcur = g;
+        if (bias) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
-      bb[h] = bias ? __ldg(reinterpret_cast<const float4*>(bias + h * 32 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    int it = 0;
-    for (int t = t0; t < t1; ++t, ++it) {
+          for (int h = 0; h < 2; ++h) bb[h] = __ldg(reinterpret_cast<const float4*>(bias + g * 64 + h * 32 + cc * 4));
+        }
+      }
       const int yb = t % nyb, xb = (t / nyb) % nxt, n = t / (nyb * nxt);
       const int y0 = 2 * yb, px0 = xb * TW + lg * 32;
       mbar_wait(smem_u32(&acc_full[it & 1]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        float* dst = Y + (((long long)n * H + (y0 + r)) * W + px0 + pq) * 64 + cc * 4;
+        float* dst = Y + (((long long)n * H + (y0 + r)) * W + px0 + pq) * ldy + g * 64 + cc * 4;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -496,7 +506,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             const int p = 4 * i + pq;
             float4 o = *reinterpret_cast<const float4*>(stg + p * 128 + ((cc ^ (p & 7)) << 4));
             o.x += bb[h].x; o.y += bb[h].y; o.z += bb[h].z; o.w += bb[h].w;
-            if (!(dbg & 1)) *reinterpret_cast<float4*>(dst + (long long)(4 * i) * 64 + h * 32) = o;
+            if (!(dbg & 1)) *reinterpret_cast<float4*>(dst + (long long)(4 * i) * ldy + h * 32) = o;
           }
           __syncwarp();
         }
@@ -538,13 +548,15 @@ __global__ void __launch_bounds__(192, 1)
 conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                          const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
                          float* __restrict__ dWt, float* __restrict__ partial, int H, int W, int total_tiles,
-                         int tiles_per_cta, int single) {
+                         int tiles_per_cta, int single, int ngroups) {
+  // C_out = 64 * ngroups: CTA b accumulates the 64-channel dY group g = b % ngroups over the pixel tiles of slot b / ngroups
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) unsigned long long bar_done, bar_full[WG_NSTAGE], bar_empty[WG_NSTAGE];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int t0 = blockIdx.x * tiles_per_cta;
+  const int grp = blockIdx.x % ngroups, ldw = 64 * ngroups;
+  const int t0 = (blockIdx.x / ngroups) * tiles_per_cta;
   int t1 = t0 + tiles_per_cta;
   if (t1 > total_tiles) t1 = total_tiles;
   const int nt = t1 - t0;
@@ -583,8 +595,8 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
         mbar_expect_tx(bar, (single ? 1u : 2u) * ((uint32_t)(WG_HALO_ROWS * 128) + 64u * 128u));
         tma_load_4d(st, &tmXh, bar, 0, xs * 64 - 1, y - 1, n);
         if (!single) tma_load_4d(st + WG_X_PLANE, &tmXl, bar, 0, xs * 64 - 1, y - 1, n);
-        tma_load_4d(st + 2 * WG_X_PLANE, &tmGh, bar, 0, xs * 64, y, n);
-        if (!single) tma_load_4d(st + 2 * WG_X_PLANE + 64 * 128, &tmGl, bar, 0, xs * 64, y, n);
+        tma_load_4d(st + 2 * WG_X_PLANE, &tmGh, bar, grp * 64, xs * 64, y, n);
+        if (!single) tma_load_4d(st + 2 * WG_X_PLANE + 64 * 128, &tmGl, bar, grp * 64, xs * 64, y, n);
       }
     }
   } else if (warp == 1) {
@@ -636,7 +648,7 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * 64 + c16 * 16), v);
         if (tap < 9) {
-          const long long off = ((long long)(tap * 64 + (m & 63))) * 64 + c16 * 16;
+          const long long off = ((long long)(tap * 64 + (m & 63))) * 64 + c16 * 16;       // inside a [576][64] tile
           if (partial) {       // per-CTA partial tile, summed by wgrad_reduce_kernel (no same-address atomics)
             float4* dst = reinterpret_cast<float4*>(partial + (long long)blockIdx.x * (576 * 64) + off);
 #pragma unroll
@@ -644,7 +656,7 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
               dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                    __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
           } else {
-            float* dst = dWt + off;
+            float* dst = dWt + ((long long)(tap * 64 + (m & 63))) * ldw + grp * 64 + c16 * 16;
 #pragma unroll
             for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
           }
@@ -659,12 +671,15 @@ conv3x3_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
+// out[k][64 g + c] = sum over the CTAs b = j * ngroups + g of partial[b][k][c]   (ngroups = 1: a plain sum of tiles)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int nslots, int ngroups) {
+  const int n = 576 * 64;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n * ngroups) return;
+  const int g = i / n, r = i - g * n;
   float a = 0.f;
-  for (int c = 0; c < nparts; ++c) a += partial[(long long)c * n + i];
-  out[i] = a;
+  for (int j = 0; j < nslots; ++j) a += partial[(long long)(j * ngroups + g) * n + r];
+  out[(long long)(r >> 6) * (64 * ngroups) + g * 64 + (r & 63)] = a;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -685,24 +700,27 @@ static inline long long rup8(long long x) { return (x + 7) & ~7LL; }
 
 }  // namespace
 
-// conv3x3 64->64 through the TMA kernel.  Returns 0 ok, 1 error, -1 not eligible (caller falls through).
+// conv3x3 64 -> Cout (64, 128, 192 or 256) through the TMA kernel.  Returns 0 ok, 1 error, -1 not eligible (caller
+// falls through).  Cout > 64 needs the persistent rolling-halo kernel (mode 3).
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
-                            int single, int a_valid, void* ws, long long ws_bytes, cudaStream_t st) {
+                            int Cout, int single, int a_valid, void* ws, long long ws_bytes, cudaStream_t st) {
   static const int mode = []() {          // TATT_TMA: 0 = off, 1 / 2 = one tile per CTA (base_offset 0 / from address),
     const char* e = getenv("TATT_TMA");   //           3 = persistent rolling-halo kernel (default)
     return e ? atoi(e) : 3;
   }();
   if (mode == 0 || ws == nullptr || W % TW != 0 || H % 2 != 0) return -1;
+  if (Cout % 64 != 0 || Cout < 64 || Cout > 256 || (Cout != 64 && mode != 3)) return -1;
+  const int ngroups = Cout / 64;
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;
   const long long P = (long long)nimg * H * W;
-  const long long nA = rup8(P * 64), nB = rup8(64LL * 576);
+  const long long nA = rup8(P * 64), nB = rup8((long long)Cout * 576);
   if ((long long)sizeof(__nv_bfloat16) * 2 * (nA + nB) > ws_bytes || (((uintptr_t)ws) & 15)) return -1;
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16 *Ahi = base, *Alo = base + nA, *Bhi = base + 2 * nA, *Blo = base + 2 * nA + nB;
   int rc = a_valid ? 0 : tatt_tc2_split(X, 64, P, 64, 0, Ahi, Alo, nullptr, st);   // activations -> [P][64] planes
   if (rc) return rc;
-  rc = tatt_tc2_split(Wt, 64, 576, 64, 1, Bhi, Blo, nullptr, st);            // Wt[576][64] -> planes [64 co][576 k]
+  rc = tatt_tc2_split(Wt, Cout, 576, Cout, 1, Bhi, Blo, nullptr, st);        // Wt[576][Cout] -> planes [Cout co][576 k]
   if (rc) return rc;
 
   constexpr int R = 2;
@@ -720,7 +738,7 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
     }
   }
   {
-    cuuint64_t gdim[2] = {576, 64};
+    cuuint64_t gdim[2] = {576, (cuuint64_t)Cout};
     cuuint64_t gstr[1] = {576 * 2};
     cuuint32_t box[2] = {64, 64};
     cuuint32_t estr[2] = {1, 1};
@@ -736,7 +754,7 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
     const int ntiles = nimg * (H / 2) * (W / TW);
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = ntiles < nsm ? ntiles : nsm;
+    const int grid = ntiles * ngroups < nsm ? ntiles * ngroups : nsm;
     // timing-experiment switches of the kernel (1: skip the global stores, 2: load the weight taps once) produce WRONG
     // results by design; they are reachable only in builds with -DTATT_ROLL_EXPERIMENTS
 #ifdef TATT_ROLL_EXPERIMENTS
@@ -753,13 +771,13 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
     }();
     if (single) {
       TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<true, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
+      conv3x3_roll_kernel<true, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups);
     } else if (cat_on) {
       TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<false, true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
+      conv3x3_roll_kernel<false, true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups);
     } else {
       TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<false, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg);
+      conv3x3_roll_kernel<false, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups);
     }
     TATT_LAUNCH_CHECK("conv3x3_roll_kernel");
     return 0;
@@ -774,41 +792,48 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
 }
 
 // conv3x3 64->64 weight gradient through the TMA kernel; dWt must be zeroed by the caller.  Same return convention.
-int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int single,
-                                  int a_valid, void* ws, long long ws_bytes, cudaStream_t st) {
+int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cout,
+                                  int single, int a_valid, void* ws, long long ws_bytes, cudaStream_t st) {
   static const int mode = []() {
     const char* e = getenv("TATT_TMA_WGRAD");
     return e ? atoi(e) : 1;
   }();
   if (mode == 0 || ws == nullptr || W % 64 != 0) return -1;
+  if (Cout % 64 != 0 || Cout < 64 || Cout > 256) return -1;
+  const int ngroups = Cout / 64;
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;
   const long long P = (long long)nimg * H * W;
-  const long long nA = rup8(P * 64);
-  const long long plane_bytes = (long long)sizeof(__nv_bfloat16) * 4 * nA;
+  const long long nA = rup8(P * 64), nG = rup8(P * Cout);
+  const long long plane_bytes = (long long)sizeof(__nv_bfloat16) * 2 * (nA + nG);
   if (plane_bytes > ws_bytes || (((uintptr_t)ws) & 15)) return -1;
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ws);
-  __nv_bfloat16 *Xh = base, *Xl = base + nA, *Gh = base + 2 * nA, *Gl = base + 3 * nA;
+  __nv_bfloat16 *Xh = base, *Xl = base + nA, *Gh = base + 2 * nA, *Gl = base + 2 * nA + nG;
   int rc = a_valid ? 0 : tatt_tc2_split(X, 64, P, 64, 0, Xh, Xl, nullptr, st);
   if (rc) return rc;
-  rc = tatt_tc2_split(dY, 64, P, 64, 0, Gh, Gl, nullptr, st);
+  rc = tatt_tc2_split(dY, Cout, P, Cout, 0, Gh, Gl, nullptr, st);
   if (rc) return rc;
   CUtensorMap tm[4];
-  cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
-  cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   cuuint32_t boxX[4] = {64, 66, 3, 1}, boxG[4] = {64, 64, 1, 1};
   void* ptrs[4] = {Xh, Xl, Gh, Gl};
   for (int i = 0; i < 4; ++i) {
+    const cuuint64_t ch = i < 2 ? 64 : (cuuint64_t)Cout;
+    cuuint64_t gdim[4] = {ch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    cuuint64_t gstr[3] = {ch * 2, (cuuint64_t)W * ch * 2, (cuuint64_t)H * W * ch * 2};
     CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptrs[i], gdim, gstr, i < 2 ? boxX : boxG, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return tatt_set_error("cuTensorMapEncodeTiled(wgrad) failed: %d", (int)r);
   }
   const int total = (int)(P / 64);
-  int grid = total < 148 ? total : 148;
-  const int per = (total + grid - 1) / grid;
-  grid = (total + per - 1) / per;
+  int dev = 0, nsm = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  int slots = nsm / ngroups;                       // CTAs per output-channel group; ngroups * slots <= #SMs
+  if (slots > total) slots = total;
+  const int per = (total + slots - 1) / slots;
+  slots = (total + per - 1) / per;
+  const int grid = slots * ngroups;
   const int smem = WG_NSTAGE * WG_STAGE + 1024;
   // per-CTA partial tiles live behind the planes when the workspace is large enough
   float* partial = nullptr;
@@ -816,10 +841,11 @@ int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, i
   if (ws_bytes >= plane_bytes + part_bytes + 16)
     partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + ((plane_bytes + 15) & ~15LL));
   TATT_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  conv3x3_wgrad_tma_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tm[3], dWt, partial, H, W, total, per, single);
+  conv3x3_wgrad_tma_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tm[3], dWt, partial, H, W, total, per, single,
+                                                    ngroups);
   TATT_LAUNCH_CHECK("conv3x3_wgrad_tma_kernel");
   if (partial) {
-    wgrad_reduce_kernel<<<(576 * 64 + 255) / 256, 256, 0, st>>>(partial, dWt, grid, 576 * 64);
+    wgrad_reduce_kernel<<<(576 * 64 * ngroups + 255) / 256, 256, 0, st>>>(partial, dWt, slots, ngroups);
     TATT_LAUNCH_CHECK("wgrad_reduce_kernel");
   }
   return 0;

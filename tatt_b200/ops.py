@@ -43,6 +43,23 @@ class full_fp32:
         _precision_flag = self._old
 
 
+class precision_flag_scope:
+    """Run the enclosed GEMMs / convolutions with the given precision flag (0 = fp32 parity on tensor cores,
+    F_BF16, F_FP32) regardless of the global mode."""
+
+    def __init__(self, flag: int):
+        self.flag = flag
+
+    def __enter__(self):
+        global _precision_flag
+        self._old = _precision_flag
+        _precision_flag = self.flag
+
+    def __exit__(self, *a):
+        global _precision_flag
+        _precision_flag = self._old
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -668,6 +685,39 @@ def tps_sample_bwd(x: Tensor, ctrl: Tensor, invk: Tensor, repr_: Tensor, dout: T
 def memcpy(dst: Tensor, src: Tensor) -> None:
     assert dst.numel() * dst.element_size() == src.numel() * src.element_size()
     _cabi.call("tatt_memcpy_d2d", _p(dst), _p(src), src.numel() * src.element_size(), _stream())
+
+
+_pack_tables: dict = {}
+
+
+def packed(srcs: Sequence[Tensor], like: Tensor, want_flat: bool = False):
+    """Copies of the (small, contiguous fp32) tensors `srcs` laid out back to back in ONE fresh buffer, made by ONE
+    kernel launch (tatt_multi_copy) instead of one memcpy node per tensor; returns views shaped like the sources.
+    Sources whose sizes are multiples of 4 end up densely concatenated (neighbouring views can be re-viewed as one
+    tensor).  The {address, offset, count} table is cached per source-address tuple and staged through pinned host
+    memory, so the first use is legal inside a CUDA-graph capture."""
+    key = tuple(t.data_ptr() for t in srcs) + tuple(t.numel() for t in srcs) + (like.device.index,)
+    ent = _pack_tables.get(key)
+    if ent is None:
+        rows, offs, off = [], [], 0
+        for t in srcs:
+            assert t.is_contiguous() and t.dtype == torch.float32
+            n = t.numel()
+            offs.append(off)
+            for c in range(0, n, 16384):
+                rows.append((t.data_ptr() + 4 * c, off + c, min(16384, n - c)))
+            off += (n + 3) // 4 * 4
+        host = torch.tensor(rows, dtype=torch.int64).pin_memory()
+        dev = torch.empty(len(rows), 3, dtype=torch.int64, device=like.device)
+        dev.copy_(host, non_blocking=True)
+        if len(_pack_tables) > 4096:
+            _pack_tables.clear()
+        ent = _pack_tables[key] = (dev, host, offs, off, len(rows))
+    dev, _, offs, total, nrows = ent
+    flat = torch.empty(total, dtype=torch.float32, device=like.device)
+    _cabi.call("tatt_multi_copy", _p(dev), nrows, _p(flat), None, _stream())
+    views = [flat[o:o + t.numel()].view(t.shape) for o, t in zip(offs, srcs)]
+    return (views, flat) if want_flat else views
 
 
 def zeros(*shape, like: Tensor) -> Tensor:

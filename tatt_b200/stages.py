@@ -54,11 +54,7 @@ class StageFn(torch.autograd.Function):
         for (raw, to_raw), g in zip(ctx.outs_raw, gouts):
             if g is not None:
                 tape.seed(raw, to_raw(g))
-        if getattr(tape, "fp32", False):
-            with ops.full_fp32():
-                tape.backward()
-        else:
-            tape.backward()
+        tape.backward()
         grads = []
         for i, spec in enumerate(ctx.ins):
             g = None
@@ -183,12 +179,11 @@ def rpe_stage(init_factor: torch.nn.Embedding, gru: torch.nn.GRU, N: int, H: int
         X = ops.empty(Wd, I, like=emb)
         _cabi.call("tatt_rpe_gather", emb.data_ptr(), X.data_ptr(), H, W, C, st())
         GI = ops.empty(2, Wd, 3 * Hd, like=emb)
-        WHH = ops.empty(2, 3 * Hd, Hd, like=emb)
-        BHH = ops.empty(2, 3 * Hd, like=emb)
         for d in range(2):
             ops.linear_fwd(X, w_ih[d], b_ih[d], out=GI[d])
-            ops.memcpy(WHH[d], w_hh[d])
-            ops.memcpy(BHH[d], b_hh[d])
+        _, pk = ops.packed([w_hh[0], w_hh[1], b_hh[0], b_hh[1]], emb, want_flat=True)   # one launch, not 4 memcpy nodes
+        WHH = pk[:2 * 3 * Hd * Hd].view(2, 3 * Hd, Hd)
+        BHH = pk[2 * 3 * Hd * Hd:].view(2, 3 * Hd)
         HALL = ops.zeros(2, N + 1, Wd, Hd, like=emb)
         GATES = ops.empty(N, 2, Wd, 4, Hd, like=emb) if tape.record else None
         GH = ops.empty(2, Wd, 3 * Hd, like=emb)
@@ -400,6 +395,9 @@ def tail_stage(seq: torch.nn.Sequential, skip_a: Tensor, skip_b: Tensor, out_pla
 
 
 # ----------------------------------------------------------------------------- STN + TPS (a3, a4)
+_stn_tc = __import__("os").environ.get("TATT_STN_TC", "1") != "0"
+
+
 def stn_tps_stage(stn_head: torch.nn.Module, tps: torch.nn.Module, x: Tensor, training: bool):
     """STNHead.forward (stn_head.py:92-106) + TPSSpatialTransformer.forward
     (tps_spatial_transformer.py:97-112).  Returns the warped image as an NHWC4-backed NCHW view."""
@@ -407,43 +405,44 @@ def stn_tps_stage(stn_head: torch.nn.Module, tps: torch.nn.Module, x: Tensor, tr
     pools = {0: (2, 2), 2: (2, 2), 4: (2, 2), 6: (2, 2), 8: (1, 2)}
 
     def build(tape: Tape, t):
-        tape.fp32 = True                       # backward closures run under the same precision mode
-        with ops.full_fp32():
-            return _build(tape, t)
-
-    def _build(tape: Tape, t):
         xin = ops._chk(t[0].contiguous(), "input image")
         N, Cin, H, W = xin.shape
         x4 = ops.nchw_to_nhwc(xin, 4)
         h = x4
-        for i in (0, 2, 4, 6, 8, 10):
-            blk = stn_head.stn_convnet[i]
-            h = tape.conv(h, blk[0].weight, blk[0].bias, 1, need_dx=(i != 0))
-            h = tape.batchnorm(h, blk[1], ops.ACT_RELU, training)
-            if i in pools:
-                h = tape.maxpool(h, *pools[i])
-        n_, hh, ww, cc = h.shape
-        flat = tape.view(tape.to_nchw(h, cc), N, cc * hh * ww)     # NCHW flatten order (stn_head.py:95)
-        fc1, bn1 = stn_head.stn_fc1[0], stn_head.stn_fc1[1]
-        if flat.shape[1] != fc1.weight.shape[1]:
-            raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (
-                N, flat.shape[1], fc1.weight.shape[1], fc1.weight.shape[0]))
-        f = tape.linear(flat, fc1.weight, fc1.bias)
-        if training and N < 2:
-            raise ValueError("Expected more than 1 value per channel when training, got input size %s" % (
-                [N, f.shape[1]],))
-        f = tape.batchnorm(f, bn1, ops.ACT_RELU, training)
-        c = tape.linear(tape.scale(f, 0.1), stn_head.stn_fc2.weight, stn_head.stn_fc2.bias)   # [N, 40]
-        if tuple(tps.target_coordinate_repr.shape) != (H * W, 23):
-            raise RuntimeError("TPS grid was built for a different output size")
-        invk, rep = tps.inverse_kernel.contiguous(), tps.target_coordinate_repr.contiguous()
-        warped, _ = ops.tps_sample_fwd(x4, c, invk, rep)
+        # the localisation convnet runs on the tensor-core engines like the trunk (fp32 parity via the bf16 hi/lo split)
+        # unless TATT_STN_TC=0; the head from fc1 on stays on the fp32 FFMA kernels: BatchNorm1d over the N samples
+        # of the batch divides by a tiny batch deviation and amplifies operand rounding of fc1 by orders of magnitude
+        conv_scope = tape.precision_scope(0) if _stn_tc else tape.fp32_scope()      # never single-plane bf16
+        with conv_scope:
+            for i in (0, 2, 4, 6, 8, 10):
+                blk = stn_head.stn_convnet[i]
+                h = tape.conv(h, blk[0].weight, blk[0].bias, 1, need_dx=(i != 0))
+                h = tape.batchnorm(h, blk[1], ops.ACT_RELU, training)
+                if i in pools:
+                    h = tape.maxpool(h, *pools[i])
+        with tape.fp32_scope():
+            n_, hh, ww, cc = h.shape
+            flat = tape.view(tape.to_nchw(h, cc), N, cc * hh * ww)     # NCHW flatten order (stn_head.py:95)
+            fc1, bn1 = stn_head.stn_fc1[0], stn_head.stn_fc1[1]
+            if flat.shape[1] != fc1.weight.shape[1]:
+                raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (
+                    N, flat.shape[1], fc1.weight.shape[1], fc1.weight.shape[0]))
+            f = tape.linear(flat, fc1.weight, fc1.bias)
+            if training and N < 2:
+                raise ValueError("Expected more than 1 value per channel when training, got input size %s" % (
+                    [N, f.shape[1]],))
+            f = tape.batchnorm(f, bn1, ops.ACT_RELU, training)
+            c = tape.linear(tape.scale(f, 0.1), stn_head.stn_fc2.weight, stn_head.stn_fc2.bias)   # [N, 40]
+            if tuple(tps.target_coordinate_repr.shape) != (H * W, 23):
+                raise RuntimeError("TPS grid was built for a different output size")
+            invk, rep = tps.inverse_kernel.contiguous(), tps.target_coordinate_repr.contiguous()
+            warped, _ = ops.tps_sample_fwd(x4, c, invk, rep)
 
-        def bwd():
-            dw = tape.grad(warped)
-            if dw is not None:
-                tape.add_grad(c, ops.tps_sample_bwd(x4, c, invk, rep, dw))
-        tape._push(bwd)
+            def bwd():
+                dw = tape.grad(warped)
+                if dw is not None:
+                    tape.add_grad(c, ops.tps_sample_bwd(x4, c, invk, rep, dw))
+            tape._push(bwd)
         return [fmap_out(warped)], [In(None)] + [In(p) for p in ps]
 
     return run_stage(build, [x] + ps)

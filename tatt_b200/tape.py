@@ -21,6 +21,7 @@ class Tape:
         self._ops: List = []
         self._g: Dict[int, Tensor] = {}
         self._keep: List[Tensor] = []
+        self._pflag = None            # inside precision_scope(flag): forward ops AND their backward closures run in that mode
 
     # ------------------------------------------------------------------ gradient bookkeeping
     def grad(self, t: Tensor) -> Optional[Tensor]:
@@ -46,7 +47,32 @@ class Tape:
 
     def _push(self, fn) -> None:
         if self.record:
+            if self._pflag is not None:
+                inner, flag = fn, self._pflag
+
+                def fn():
+                    with ops.precision_flag_scope(flag):
+                        inner()
             self._ops.append(fn)
+
+    def precision_scope(self, flag: int):
+        """Context manager: the ops recorded inside AND their backward closures run with precision flag `flag`
+        (0 = fp32 parity on tensor cores, ops.F_FP32 = fp32 FFMA kernels, ops.F_BF16), whatever the global mode is."""
+        tape = self
+
+        class _Scope:
+            def __enter__(self):
+                self.prev, tape._pflag = tape._pflag, flag
+                self.ctx = ops.precision_flag_scope(flag)
+                self.ctx.__enter__()
+
+            def __exit__(self, *a):
+                self.ctx.__exit__(*a)
+                tape._pflag = self.prev
+        return _Scope()
+
+    def fp32_scope(self):
+        return self.precision_scope(ops.F_FP32)
 
     # ------------------------------------------------------------------ dense layers
     def _split_grad(self, dy: Tensor, bias: Optional[Tensor]):
@@ -321,15 +347,13 @@ class Tape:
         w_hh = (gru.weight_hh_l0, gru.weight_hh_l0_reverse)
         b_ih = (gru.bias_ih_l0, gru.bias_ih_l0_reverse)
         b_hh = (gru.bias_hh_l0, gru.bias_hh_l0_reverse)
-        wih = ops.empty(192, 64, like=c)          # both directions' input projections as ONE N=192 GEMM
-        bih = ops.empty(192, like=c)
-        whh = ops.empty(2, 96, 32, like=c)
-        bhh = ops.empty(2, 96, like=c)
-        for d in range(2):
-            ops.memcpy(wih[d * 96:(d + 1) * 96], w_ih[d])
-            ops.memcpy(bih[d * 96:(d + 1) * 96], b_ih[d])
-            ops.memcpy(whh[d], w_hh[d])
-            ops.memcpy(bhh[d], b_hh[d])
+        # both directions' weights side by side (input projections as ONE N=192 GEMM): one pack launch, 8 sources
+        _, flat = ops.packed([w_ih[0], w_ih[1], b_ih[0], b_ih[1], w_hh[0], w_hh[1], b_hh[0], b_hh[1]], c, want_flat=True)
+        assert flat.numel() == 18816                                         # dense: every source size is a multiple of 4
+        wih = flat[0:12288].view(192, 64)
+        bih = flat[12288:12480]
+        whh = flat[12480:18624].view(2, 96, 32)
+        bhh = flat[18624:18816].view(2, 96)
         rows = ops.rows_gemm_ok(P, 64, 192) and ops.rows_gemm_ok(P, 192, 64) and ops.rows_wgrad_ok(P, 192, 64)
         cP = ops.split_matrix(c) if (self.record and not rows) else None
         gi = ops.linear_fwd(c, wih, bih, xP=cP)
