@@ -79,7 +79,9 @@ int tatt_rows_wgrad(const float* A, long long lda, int a_off0, int a_off1, const
  * data-gradient, to the flipped/transposed Wt[(ky,kx,co)][ci] (flip=1).
  * flags of tatt_conv2d_igemm / tatt_conv2d_wgrad: 1 / 2 / 128 / 1024 as for tatt_gemm; 2048: the bf16 planes of X at the start of
  * `ws` are still valid from an earlier call on the same X (forward -> weight gradient, or the dY planes the weight-gradient
- * pass leaves behind the X planes -> data gradient with ws advanced past the X planes): skip the split pass. */
+ * pass leaves behind the X planes -> data gradient with ws advanced past the X planes): skip the split pass.
+ * 4096 (tatt_conv2d_wgrad, 3x3 / 64 input channels only): the dY planes behind the X planes were already written by the
+ * caller (tatt_split_bf16 to ws + 4 * round8(|X|) bytes, lo plane round8(|dY|) elements later). */
 int tatt_conv_weight_pack(const float* W, float* Wt, int Cout, int Cin, int KH, int KW, int CinP, int CoutP,
                           int flip, void* stream);
 int tatt_conv_weight_unpack_grad(const float* dWt, float* dW, int Cout, int Cin, int KH, int KW, int CinP,

@@ -736,9 +736,10 @@ int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int
   if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout % 64 == 0 && Cout <= 256 && ws &&
       !(flags & F_FP32)) {
     int rc = tatt_tc3_conv3x3_wgrad_launch(X, dY, dWt, nimg, H, W, Cout, (flags & F_BF16) ? 1 : 0,
-                                           (flags & F_A_VALID) ? 1 : 0, ws, ws_bytes, st);
+                                           (flags & F_A_VALID) ? 1 : 0, (flags & F_B_VALID) ? 1 : 0, ws, ws_bytes, st);
     if (rc >= 0) return rc;
   }
+  // (flag 4096 is a hint for the TMA kernel only: the generic engine below splits dY itself)
   GemmP p = {};
   p.A = X; p.B = dY; p.C = dWt; p.bias = nullptr;
   p.M = KH * KW * Cin; p.N = Cout; p.K = nimg * H * W;

@@ -29,7 +29,7 @@ __device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
 
 enum { A_ROW = 0, A_COL = 1, A_IM2COL = 2, A_IM2COL_T = 3 };
 enum { B_KN = 0, B_NK = 1 };
-enum { F_ACCUM = 1, F_RELU = 2, F_ATOMIC = 4, F_VECA = 8, F_VECB = 16, F_VECC = 32, F_ZEROC = 64, F_FP32 = 128, F_APLANES = 256, F_BPLANES = 512, F_BF16 = 1024, F_A_VALID = 2048 };
+enum { F_ACCUM = 1, F_RELU = 2, F_ATOMIC = 4, F_VECA = 8, F_VECB = 16, F_VECC = 32, F_ZEROC = 64, F_FP32 = 128, F_APLANES = 256, F_BPLANES = 512, F_BF16 = 1024, F_A_VALID = 2048, F_B_VALID = 4096 };
 
 struct GemmP {
   const float* A;
@@ -63,4 +63,4 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
                             int Cout, int single, int a_valid, void* ws, long long ws_bytes, cudaStream_t st);
 int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cout,
-                                  int single, int a_valid, void* ws, long long ws_bytes, cudaStream_t st);
+                                  int single, int a_valid, int b_valid, void* ws, long long ws_bytes, cudaStream_t st);

@@ -793,7 +793,7 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
 
 // conv3x3 64->64 weight gradient through the TMA kernel; dWt must be zeroed by the caller.  Same return convention.
 int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cout,
-                                  int single, int a_valid, void* ws, long long ws_bytes, cudaStream_t st) {
+                                  int single, int a_valid, int b_valid, void* ws, long long ws_bytes, cudaStream_t st) {
   static const int mode = []() {
     const char* e = getenv("TATT_TMA_WGRAD");
     return e ? atoi(e) : 1;
@@ -811,7 +811,7 @@ int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, i
   __nv_bfloat16 *Xh = base, *Xl = base + nA, *Gh = base + 2 * nA, *Gl = base + 2 * nA + nG;
   int rc = a_valid ? 0 : tatt_tc2_split(X, 64, P, 64, 0, Xh, Xl, nullptr, st);
   if (rc) return rc;
-  rc = tatt_tc2_split(dY, Cout, P, Cout, 0, Gh, Gl, nullptr, st);
+  rc = b_valid ? 0 : tatt_tc2_split(dY, Cout, P, Cout, 0, Gh, Gl, nullptr, st);     // b_valid: the caller split dY already
   if (rc) return rc;
   CUtensorMap tm[4];
   cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -835,11 +835,14 @@ int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, i
   slots = (total + per - 1) / per;
   const int grid = slots * ngroups;
   const int smem = WG_NSTAGE * WG_STAGE + 1024;
-  // per-CTA partial tiles live behind the planes when the workspace is large enough
+  // per-CTA partial tiles live behind the planes when the workspace is large enough -- and behind the slot right after
+  // the dY planes where the data-gradient pass of the same layer (which reuses the dY planes, F_A_VALID with the
+  // workspace advanced past the X planes) puts its weight planes: that pass may run concurrently on another stream
   float* partial = nullptr;
+  const long long part_off = ((plane_bytes + 4 * rup8(576LL * Cout) + 64 + 15) & ~15LL);
   const long long part_bytes = (long long)grid * 576 * 64 * sizeof(float);
-  if (ws_bytes >= plane_bytes + part_bytes + 16)
-    partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + ((plane_bytes + 15) & ~15LL));
+  if (ws_bytes >= part_off + part_bytes + 16)
+    partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + part_off);
   TATT_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   conv3x3_wgrad_tma_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tm[3], dWt, partial, H, W, total, per, single,
                                                     ngroups);

@@ -64,6 +64,53 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- side stream for work that is off the critical path of the backward pass (weight gradients): the data-gradient
+# chain of a stage is a serial sequence of mostly latency- / HBM-latency-bound kernels, the weight-gradient kernels
+# only feed the optimizer.  Inside `with side_stream():` launches go to a per-device second stream that first waits
+# for everything enqueued on the caller's stream so far; `join_side()` makes the caller's stream wait for it.  Both
+# are plain event edges, so a CUDA-graph capture turns them into a fork / join of the graph.  TATT_SIDE=0 disables it.
+_side_enabled = os.environ.get("TATT_SIDE", "1") != "0"
+_side_streams: dict = {}
+_side_dirty: dict = {}
+
+
+class side_stream:
+    def __enter__(self):
+        self.ctx = None
+        if not _side_enabled:
+            return self
+        cur = torch.cuda.current_stream()
+        dev = cur.device_index
+        s = _side_streams.get(dev)
+        if s is None:
+            s = _side_streams[dev] = torch.cuda.Stream(device=dev)
+        if cur == s:                                  # nested use: already on the side stream
+            return self
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        s.wait_event(ev)
+        _side_dirty[dev] = True
+        self.ctx = torch.cuda.stream(s)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+        return False
+
+
+def join_side() -> None:
+    """the current stream waits for everything launched on its device's side stream"""
+    cur = torch.cuda.current_stream()
+    dev = cur.device_index
+    if _side_dirty.get(dev):
+        ev = torch.cuda.Event()
+        ev.record(_side_streams[dev])
+        cur.wait_event(ev)
+        _side_dirty[dev] = False
+
+
 # Bumped whenever parameters are updated through raw pointers (the fused clip+Adam kernel writes the flat parameter
 # buffer without touching torch's version counters); caches derived from weights key on it (tsrn.TPInterpreter).
 _weights_epoch = 0
@@ -396,14 +443,31 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Option
     return y
 
 
+F_B_VALID = 4096
+
+
+class _NoSide:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True, need_dw: bool = True,
-               has_bias: bool = True, keep: Optional[dict] = None):
-    """-> (dx [N,H,W,CinP] | None, dW [Cout,Cin,KH,KW] | None, db [Cout] | None)"""
+               has_bias: bool = True, keep: Optional[dict] = None, side=None):
+    """-> (dx [N,H,W,CinP] | None, dW [Cout,Cin,KH,KW] | None, db [Cout] | None).
+    `side(*reads)` (optional, the tape's) returns a context manager that runs the enclosed launches on the side
+    stream: the weight gradient (and the bias gradient) only feed the optimizer, so they run there, concurrently with
+    the data gradient.  The two passes then never share scratch: the 3x3 / 64-channel layers split dY ONCE on the
+    caller's stream (planes behind the X planes, bias gradient from the same pass) and both passes read them; every
+    other layer gives the data-gradient pass its own workspace."""
     n, h, wd, cin_p = x.shape
     co, ci, kh, kw = w.shape
     cout_p = dy.shape[-1]
     P = n * h * wd
     dx = dw = db = None
+    on_side = side if side is not None else (lambda *r: _NoSide())
     kx = cout_p == 4 and kw > 1 and cin_p >= 16
     ndy = P * _r8(kw * 4) if kx else P * _r8(cout_p)
     extra = (kh * cin_p * _r8(kw * 4) + 148 * kh * cin_p * _r8(kw * 4)) if kx else (
@@ -414,33 +478,55 @@ def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True,
     if ws is None:
         ws = _conv_ws(x, x.numel(), ndy, extra)
     wsb = 0 if ws is None else ws.numel()
+    # 3x3 convolutions with 64 input channels: both backward passes run on the plane engines and share the dY planes
+    share = (ws is not None and _conv_share_dy and not kx and kh == 3 and kw == 3 and cin_p == 64
+             and cout_p in (64, 128, 192, 256) and P >= 128)
+    dy2 = dy.view(-1, cout_p)
     dy_valid = False
+    if share and need_dw and wd % 64 == 0:
+        # one split of dY on this stream serves both passes; its column sums are the bias gradient
+        off = 4 * _r8(x.numel())
+        dbp = empty(cout_p, like=x) if has_bias else None
+        _cabi.call("tatt_split_bf16", _p(dy2), cout_p, P, cout_p, 0, ws.data_ptr() + off,
+                   ws.data_ptr() + off + 2 * _r8(P * cout_p), _p(dbp), _stream())
+        if has_bias:
+            db = dbp[:co]
+        dy_valid = True
     if need_dw and kx:
-        dt = empty(P, kw * 4, like=x)
-        _cabi.call("tatt_conv_kxexp_expand", _p(dy), _p(dt), P, wd, kw, 4, pad, _stream())
-        dwte = empty(kh * cin_p, kw * 4, like=x)
-        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dt), _p(dwte), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0,
-                   _precision_flag | (F_A_VALID if x_valid else 0), _p(ws), wsb, _stream())
-        dw = empty(co, ci, kh, kw, like=x)
-        _cabi.call("tatt_conv_kxexp_unpack_grad", _p(dwte), _p(dw), co, ci, kh, kw, cin_p, 4, _stream())
-        if has_bias:
-            db = colsum(dy.view(-1, cout_p))[:co]
+        with on_side(x, dy, ws):
+            dt = empty(P, kw * 4, like=x)
+            _cabi.call("tatt_conv_kxexp_expand", _p(dy), _p(dt), P, wd, kw, 4, pad, _stream())
+            dwte = empty(kh * cin_p, kw * 4, like=x)
+            _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dt), _p(dwte), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0,
+                       _precision_flag | (F_A_VALID if x_valid else 0), _p(ws), wsb, _stream())
+            dw = empty(co, ci, kh, kw, like=x)
+            _cabi.call("tatt_conv_kxexp_unpack_grad", _p(dwte), _p(dw), co, ci, kh, kw, cin_p, 4, _stream())
+            if has_bias:
+                db = colsum(dy2)[:co]
     elif need_dw:
-        dwt = empty(kh * kw * cin_p, cout_p, like=x)
-        _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dy), _p(dwt), n, h, wd, cin_p, cout_p, kh, kw, pad, pad,
-                   _precision_flag | (F_A_VALID if x_valid else 0), _p(ws), wsb, _stream())
-        # the tcgen05 weight-gradient kernels leave the dY planes right behind the X planes
-        dy_valid = (ws is not None and _conv_share_dy and kh == 3 and kw == 3 and cin_p == 64 and cout_p in (64, 256)
-                    and P >= 128)
-        dw = empty(co, ci, kh, kw, like=x)
-        _cabi.call("tatt_conv_weight_unpack_grad", _p(dwt), _p(dw), co, ci, kh, kw, cin_p, cout_p, _stream())
-        if has_bias:
-            db = colsum(dy.view(-1, cout_p))[:co]
+        with on_side(x, dy, ws):
+            dwt = empty(kh * kw * cin_p, cout_p, like=x)
+            _cabi.call("tatt_conv2d_wgrad", _p(x), _p(dy), _p(dwt), n, h, wd, cin_p, cout_p, kh, kw, pad, pad,
+                       _precision_flag | (F_A_VALID if x_valid else 0) | (F_B_VALID if dy_valid else 0), _p(ws), wsb,
+                       _stream())
+            dw = empty(co, ci, kh, kw, like=x)
+            _cabi.call("tatt_conv_weight_unpack_grad", _p(dwt), _p(dw), co, ci, kh, kw, cin_p, cout_p, _stream())
+            if has_bias and db is None:
+                db = colsum(dy2)[:co]
+        # without the shared split, the tcgen05 weight-gradient kernels still leave the dY planes behind the X planes;
+        # they are only safe to reuse when that pass ran on THIS stream
+        if share and not dy_valid and side is None:
+            dy_valid = True
     if need_dx:
         wb = conv_pack(w, cin_p, cout_p, True)
         dx = empty(n, h, wd, cin_p, like=x)
-        off = 4 * _r8(x.numel()) if dy_valid else 0            # bytes: skip the X planes
-        wsd = ws[off:] if ws is not None else None
+        if dy_valid:
+            wsd = ws[4 * _r8(x.numel()):]                       # bytes: skip the X planes
+        elif need_dw and side is not None:
+            # the weight-gradient pass owns `ws` on the side stream: separate scratch for this pass
+            wsd = _conv_ws(x, dy.numel(), 0, kh * kw * cout_p * _r8(cin_p) + 16)
+        else:
+            wsd = ws
         _cabi.call("tatt_conv2d_igemm", _p(dy), _p(wb), None, _p(dx), n, h, wd, cout_p, cin_p, kh, kw,
                    kh - 1 - pad, kw - 1 - pad, _precision_flag | (F_A_VALID if dy_valid else 0), _p(wsd),
                    0 if wsd is None else wsd.numel(), _stream())

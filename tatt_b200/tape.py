@@ -21,6 +21,7 @@ class Tape:
         self._ops: List = []
         self._g: Dict[int, Tensor] = {}
         self._keep: List[Tensor] = []
+        self._side_keep: List = []    # tensors read by side-stream kernels: kept alive until the join (see backward())
         self._pflag = None            # inside precision_scope(flag): forward ops AND their backward closures run in that mode
 
     # ------------------------------------------------------------------ gradient bookkeeping
@@ -32,6 +33,7 @@ class Tape:
             return
         k = id(t)
         if k in self._g:
+            ops.join_side()           # either addend may have been produced on the side stream
             self._g[k] = ops.add(self._g[k], g.reshape(self._g[k].shape))
         else:
             self._g[k] = g
@@ -44,6 +46,17 @@ class Tape:
     def backward(self) -> None:
         for fn in reversed(self._ops):
             fn()
+        ops.join_side()               # weight-gradient kernels launched on the side stream (see _side)
+        self._side_keep.clear()
+
+    def _side(self, *reads: Optional[Tensor]):
+        """`with self._side(t0, t1, ...):` -- run the enclosed launches on the side stream (ops.side_stream).  `reads`
+        are the tensors those kernels read: main-stream temporaries among them could otherwise be freed -- and their
+        memory reused by later main-stream work -- while the side stream still reads them, so they are kept alive
+        until backward() has joined the streams.  Tensors ALLOCATED inside the block belong to the side stream; they
+        are only consumed after the join (gradient packing / autograd accumulation)."""
+        self._side_keep.extend(t for t in reads if t is not None)
+        return ops.side_stream()
 
     def _push(self, fn) -> None:
         if self.record:
@@ -101,7 +114,8 @@ class Tape:
             if relu:
                 dy = ops.relu_bwd(y, dy)
             if rows:        # fused-split kernels: one pass over (dy, x) for dW + db, one over dy for dx
-                dW, db = ops.linear_bwd_weight_rows(dy, x, b is not None)
+                with self._side(dy, x):
+                    dW, db = ops.linear_bwd_weight_rows(dy, x, b is not None)
                 self.add_grad(W, dW)
                 if b is not None:
                     self.add_grad(b, db)
@@ -127,7 +141,8 @@ class Tape:
                 dy = self.grad(y)
                 if dy is None:
                     return
-                dW, db = ops.linear_bwd_weight_rows_parts(dy, parts, True)
+                with self._side(dy, *parts):
+                    dW, db = ops.linear_bwd_weight_rows_parts(dy, parts, True)
                 self.add_grad(W4, dW.view_as(W4))
                 self.add_grad(b, db)
                 for i, t in enumerate(parts):
@@ -171,7 +186,8 @@ class Tape:
                 return
             if relu:
                 dy = ops.relu_bwd(y, dy)
-            dx, dw, db = ops.conv2d_bwd(x4, w, dy, pad, need_dx=need_dx, has_bias=b is not None, keep=keep)
+            dx, dw, db = ops.conv2d_bwd(x4, w, dy, pad, need_dx=need_dx, has_bias=b is not None, keep=keep,
+                                        side=self._side)
             self.add_grad(w, dw)
             if b is not None:
                 self.add_grad(b, db)
@@ -366,12 +382,13 @@ class Tape:
                 return
             dgi, dgh = ops.gru32_scan_bwd(dout, gates, whh, nseq, T, s_inner, outer, inner, tstride)
             if rows:
-                dwih, dbih = ops.linear_bwd_weight_rows(dgi, c, True)          # [192, 64], [192]
-                dwhh, dbhh = ops.empty(2, 96, 32, like=c), ops.empty(192, like=c)
-                # dW_hh[d] = dgh[:, 96d:96d+96]^T h_{t-1}[d]: the saved h_{t-1} of both directions (two 32-column
-                # segments of the gate tensor) form the 64 A channels; the diagonal blocks of the product are kept
-                ops.rows_wgrad(gates, (128, 288), ops._blocks64(dgh), dwhh, 2, 96, 32, True, rb=32, cb=96,
-                               colsum_src=2, dbias=dbhh)
+                with self._side(dgi, dgh, c, gates):
+                    dwih, dbih = ops.linear_bwd_weight_rows(dgi, c, True)          # [192, 64], [192]
+                    dwhh, dbhh = ops.empty(2, 96, 32, like=c), ops.empty(192, like=c)
+                    # dW_hh[d] = dgh[:, 96d:96d+96]^T h_{t-1}[d]: the saved h_{t-1} of both directions (two 32-column
+                    # segments of the gate tensor) form the 64 A channels; the diagonal blocks of the product are kept
+                    ops.rows_wgrad(gates, (128, 288), ops._blocks64(dgh), dwhh, 2, 96, 32, True, rb=32, cb=96,
+                                   colsum_src=2, dbias=dbhh)
                 for d in range(2):
                     self.add_grad(w_hh[d], dwhh[d])
                     self.add_grad(b_hh[d], dbhh[d * 96:(d + 1) * 96])
@@ -402,10 +419,11 @@ class Tape:
         """(dW, db, dx) of y = x W^T + b for a gradient dy (row-panel kernels when the shape qualifies)"""
         M, K = x.shape
         N = W.shape[0]
-        if ops.rows_wgrad_ok(M, N, K) and ops.rows_gemm_ok(M, N, K):
-            dW, db = ops.linear_bwd_weight_rows(dy, x, True)
-        else:
-            dW, db = ops.linear_bwd_weight(dy, x), ops.colsum(dy)
+        with self._side(dy, x):
+            if ops.rows_wgrad_ok(M, N, K) and ops.rows_gemm_ok(M, N, K):
+                dW, db = ops.linear_bwd_weight_rows(dy, x, True)
+            else:
+                dW, db = ops.linear_bwd_weight(dy, x), ops.colsum(dy)
         return dW, db, (ops.linear_bwd_data(dy, W) if want_dx else None)
 
     def dec_layer(self, tgt: Tensor, qp: Tensor, kin: Tensor, mem: Tensor, d: torch.nn.Module, lnf: torch.nn.Module,
@@ -472,8 +490,9 @@ class Tape:
             dbin = ops.empty(192, like=tgt)
             for i, (g, src) in enumerate(((dq, qin), (dk, kin), (dv, mem))):
                 dW_i, db_i, dx_i = self._lin_bwd(g, src, Win[i * 64:(i + 1) * 64])
-                ops.memcpy(dWin[i * 64:(i + 1) * 64], dW_i)
-                ops.memcpy(dbin[i * 64:(i + 1) * 64], db_i)
+                with self._side(dW_i, db_i):                      # same stream as their producers
+                    ops.memcpy(dWin[i * 64:(i + 1) * 64], dW_i)
+                    ops.memcpy(dbin[i * 64:(i + 1) * 64], db_i)
                 if i == 0:
                     self.add_grad(tgt, ops.add(dx_i, dS2))
                     self.add_grad(qp, dx_i)
