@@ -100,15 +100,27 @@ class side_stream:
         return False
 
 
+_side_hold: list = []
+
+
+def hold_until_join(*tensors) -> None:
+    """keep main-stream tensors that side-stream kernels read alive until the next join_side()"""
+    _side_hold.extend(t for t in tensors if t is not None)
+
+
 def join_side() -> None:
-    """the current stream waits for everything launched on its device's side stream"""
+    """the current stream waits for everything launched on its device's side stream (no-op when called from code that
+    itself runs on the side stream)"""
     cur = torch.cuda.current_stream()
     dev = cur.device_index
+    if cur == _side_streams.get(dev):
+        return
     if _side_dirty.get(dev):
         ev = torch.cuda.Event()
         ev.record(_side_streams[dev])
         cur.wait_event(ev)
         _side_dirty[dev] = False
+    _side_hold.clear()
 
 
 # Bumped whenever parameters are updated through raw pointers (the fused clip+Adam kernel writes the flat parameter

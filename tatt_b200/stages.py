@@ -32,6 +32,10 @@ class In:
         self.key, self.from_raw = key, from_raw
 
 
+def _join_side_at_end_of_backward():
+    ops.join_side()
+
+
 class StageFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, builder, *tensors):
@@ -54,7 +58,16 @@ class StageFn(torch.autograd.Function):
         for (raw, to_raw), g in zip(ctx.outs_raw, gouts):
             if g is not None:
                 tape.seed(raw, to_raw(g))
-        tape.backward()
+        if getattr(tape, "params_only", False) and ops._side_enabled:
+            # a stage whose backward feeds parameters only (the RPE): the whole chain runs on the side stream,
+            # concurrently with whatever the engine runs next; joined when the backward pass ends (engine callback),
+            # i.e. before any optimizer / packing kernel can read the gradients
+            ops.hold_until_join(*tape._g.values())            # the seeded output gradients were made on this stream
+            with ops.side_stream():
+                tape.backward()
+            torch.autograd.Variable._execution_engine.queue_callback(_join_side_at_end_of_backward)
+        else:
+            tape.backward()
         grads = []
         for i, spec in enumerate(ctx.ins):
             g = None
@@ -258,6 +271,7 @@ def rpe_stage(init_factor: torch.nn.Embedding, gru: torch.nn.GRU, N: int, H: int
             _cabi.call("tatt_rpe_scatter", dX.data_ptr(), demb.data_ptr(), H, W, C, st())
             tape.add_grad(emb, demb)
         tape._push(bwd)
+        tape.params_only = True
         return [Out(QPOS, QPOS.view(N, H * W, C), lambda g: g.contiguous())], [In(p) for p in ps]
 
     return run_stage(build, ps)

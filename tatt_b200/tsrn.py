@@ -215,9 +215,10 @@ class TPInterpreter(nn.Module):
             self._qpos_cache = (key, fresh)
         return self._qpos_cache[1]
 
-    def forward(self, image_feature, tp_input):
+    def forward(self, image_feature, tp_input, qpos=None):
         N, C, H, W = image_feature.shape
-        qpos = self.query_pos(tp_input.shape[0], H, W)
+        if qpos is None:
+            qpos = self.query_pos(tp_input.shape[0], H, W)
         return stages.tp_stage(self, image_feature, tp_input, qpos, self.training)
 
 
@@ -384,10 +385,17 @@ class TSRN_TL_TRANS(_TSRNBase):
         self._text_emb = text_emb
 
     def forward(self, x, text_emb=None, text_emb_gt=None, feature_arcs=None, rand_offs=None):
-        block = {"1": self._stem(x)}
         if text_emb is None:
             text_emb = torch.zeros(1, self._text_emb, 1, 26, device=x.device)
-        tp_map, pr_weights = self.infoGen(block["1"], text_emb)
+        # the recurrent positional encoding depends on the weights and the batch size only: it runs on the side stream,
+        # concurrently with the STN / stem of the image branch, and is joined right before the TP interpreter needs it
+        qpos = None
+        if x.is_cuda and x.dim() == 4:
+            with stages.ops.side_stream():
+                qpos = self.infoGen.query_pos(text_emb.shape[0], x.shape[2], x.shape[3])
+        block = {"1": self._stem(x)}
+        stages.ops.join_side()
+        tp_map, pr_weights = self.infoGen(block["1"], text_emb, qpos)
         k = self.srb_nums + 2
         for i in range(2, k + 1):
             blk = getattr(self, "block%d" % i)
