@@ -100,12 +100,14 @@ class side_stream:
         return False
 
 
-_side_hold: list = []
+_side_hold: dict = {}                 # device index -> tensors (one caller thread per device, like the streams)
 
 
 def hold_until_join(*tensors) -> None:
-    """keep main-stream tensors that side-stream kernels read alive until the next join_side()"""
-    _side_hold.extend(t for t in tensors if t is not None)
+    """keep main-stream tensors that side-stream kernels read alive until the next join_side() on their device"""
+    for t in tensors:
+        if t is not None:
+            _side_hold.setdefault(t.device.index, []).append(t)
 
 
 def join_side() -> None:
@@ -120,7 +122,7 @@ def join_side() -> None:
         ev.record(_side_streams[dev])
         cur.wait_event(ev)
         _side_dirty[dev] = False
-    _side_hold.clear()
+    _side_hold.pop(dev, None)
 
 
 # Bumped whenever parameters are updated through raw pointers (the fused clip+Adam kernel writes the flat parameter

@@ -16,6 +16,8 @@ ENTRY = {
     "tc2_gemm_kernel<0, 4>": "tatt_gemm M128 N1024 K3072 x2",
     "rows_wgrad1_kernel<3>": "tatt_rows_wgrad NB3",
     "conv3x3_roll_kernel<0, 1>": "tatt_conv2d_igemm 3x3 64->64",
+    "mha_bwd_kernel": "tatt_mha64_bwd ",
+    "rpe_fwd_persist_kernel": "tatt_rpe_fwd T64 W128 Hd1024",
     "conv3x3_wgrad_tma_kernel": "tatt_conv2d_wgrad 3x3 64->64",
     "tp_declayer_fwd_kernel<1>": "tatt_tp_declayer_fwd ",
     "gru32_scan_bwd_mma_kernel<1>": "tatt_gru32_scan_bwd T128",
@@ -25,8 +27,8 @@ ENTRY = {
 }
 COLS = {"dur": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram__bytes_write.sum",
         "tensor": "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
-        "tensor2": "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
-        "dram": "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "tensor2": "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "dram": "FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "l2": "lts__t_sectors.avg.pct_of_peak_sustained_elapsed", "sm": "sm__throughput.avg.pct_of_peak_sustained_elapsed"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6,
         "ns": 1e-3, "us": 1.0, "ms": 1e3, "%": 1.0, "": 1.0}
@@ -59,19 +61,21 @@ def main():
                 v = num(r[idx[col]])
                 if v is not None:
                     a[k].append(v * UNIT.get(units[idx[col]], 1.0))
-    lines = ["# per kernel: launches captured, avg duration (us), DRAM read / written per launch (MB), tensor pipe %, DRAM %, "
-             "L2 %, SM % (ncu --set full, --clock-control none; cold-cache, serialised)",
-             "%-44s %4s %9s %9s %9s %7s %6s %6s %6s" % ("kernel", "n", "us", "rd MB", "wr MB", "tensor", "dram", "l2", "sm")]
+    lines = ["# per kernel: launches captured, avg duration (us), DRAM read / written per launch (MB), tensor pipe %, DRAM GB/s, "
+             "L2 %, SM % (ncu --set full, --clock-control none; serialised); GB/s = (read + written) / duration, copy peak 6449",
+             "%-44s %4s %9s %9s %9s %7s %6s %6s %6s" % ("kernel", "n", "us", "rd MB", "wr MB", "tensor", "GB/s", "l2", "sm")]
     js = {"_source": out_txt}
     for name, a in sorted(agg.items(), key=lambda kv: -sum(kv[1]["dur"])):
         def av(k):
             return sum(a[k]) / len(a[k]) if a[k] else float("nan")
         t = av("tensor") if a["tensor"] else av("tensor2")
         lines.append("%-44s %4d %9.1f %9.2f %9.2f %7.1f %6.1f %6.1f %6.1f" % (
-            name[:44], len(a["dur"]), av("dur"), av("rd") / 1e6, av("wr") / 1e6, t, av("dram"), av("l2"), av("sm")))
+            name[:44], len(a["dur"]), av("dur"), av("rd") / 1e6, av("wr") / 1e6, t, (av("rd") + av("wr")) / av("dur") / 1e3,
+            av("l2"), av("sm")))
         if name in ENTRY:
             js[ENTRY[name]] = {"kernel": name, "dram_bytes_per_launch": av("rd") + av("wr"), "launches": len(a["dur"]),
-                               "avg_us_under_ncu": av("dur"), "tensor_pipe_pct": t, "dram_pct": av("dram")}
+                               "avg_us_under_ncu": av("dur"), "tensor_pipe_pct": t,
+                               "dram_gbs": (av("rd") + av("wr")) / av("dur") / 1e3}
     open(out_txt, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
     if out_json:
