@@ -217,7 +217,10 @@ def step_profile(trainer, Trainer, xs, ts_, third, peaks, bf16):
     list of a step by entry point, measured live on the launching stream.  -> (top entries by share with their
     roofline fractions, total kernel seconds).  Event pairs add ~1-2 us per call; the ncu launch list of the same
     build under profiles/ is the cross-check."""
-    from tatt_b200 import _cabi
+    from tatt_b200 import _cabi, ops
+    # kernels are timed one at a time: the side stream (weight gradients overlapping the data-gradient chain) is off for
+    # this one step, otherwise concurrent kernels would stretch each other's event pairs
+    side_was, ops._side_enabled = ops._side_enabled, False
     Trainer.step(trainer, xs, ts_, third)                    # warm caches / workspaces on the eager path
     torch.cuda.synchronize()
     # An event pair brackets a HOST call: on an idle stream the first event fires at once and the pair then also counts the
@@ -229,6 +232,7 @@ def step_profile(trainer, Trainer, xs, ts_, third, peaks, bf16):
         pad.fill_(0.0)
     with _cabi.Profile() as prof:
         Trainer.step(trainer, xs, ts_, third)
+    ops._side_enabled = side_was
     del pad
     rows = prof.summary(lambda n, a: (n, entry_cost(n, a)[0]))
     total = sum(r[2] for r in rows)
@@ -410,7 +414,8 @@ def run_ours(args):
             "config": {"workload": workload_name(kw, B),
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                        "loss": "ImageLoss(gradient=True, loss_weight=[1, 1e-4])(out, hr).mean() * 100 (CUDA, csrc/loss.cu)",
-                       "launch": "eager" if args.eager else "cuda-graphs (fwd+loss+bwd+pack | allreduce | clip+Adam)",
+                       "launch": "eager" if args.eager else "cuda-graphs (fwd+loss+bwd+pack | allreduce | clip+Adam); weight "
+                                 "gradients on a side stream inside the graph (TATT_SIDE=0: single stream)",
                        "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                        "parity_note": "the timed step runs dropout 0.1 (own Philox stream); the parity-checked step is "
                                       "the same code at p = 0 (tests/test_model_gpu.py::test_benchmarked_config_vs_golden)"},

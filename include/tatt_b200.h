@@ -92,6 +92,14 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
 int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cin, int Cout,
                       int KH, int KW, int padH, int padW, int flags, void* ws, long long ws_bytes, void* stream);
 
+/* 3x3 / 64 -> 64 convolution (tsrn.py:876,884,611) that also yields the BatchNorm statistics of its output from the same
+ * pass: stats = 128 doubles {sum_c, sumsq_c} (zeroed here, fp32 partials per thread -> fp64 atomics in the epilogue of the
+ * persistent TMA kernel); tatt_bn_finalize turns them into mean / invstd (+ running statistics).  Served shapes only
+ * (tatt_conv3x3_stats_supported != 0: W % 128 == 0, H % 2 == 0); flags 1024 / 2048 as for tatt_conv2d_igemm. */
+int tatt_conv3x3_stats_supported(int H, int W, int Cin, int Cout);
+int tatt_conv3x3_stats(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W, int flags,
+                       void* ws, long long ws_bytes, void* stats, void* stream);
+
 /* 9x9 convolution with <= 4 output channels (tsrn.py:623) as a K = KH*Cin, N = KW*CoP GEMM over the vertical
  * taps (tatt_conv2d_igemm / tatt_conv2d_wgrad with KW=1) plus these horizontal shift-sum / shift-expand passes */
 int tatt_conv_kxexp_pack(const float* W, float* Wt, int Cout, int Cin, int KH, int KW, int CinP, int CoP,
@@ -108,6 +116,8 @@ int tatt_conv_kxexp_expand(const float* dOut, float* dT, long long P, int W, int
  * (model/tsrn.py:1061-1064).  ws: scratch of >= 2*C doubles. */
 int tatt_bn_stats(const float* X, long long P, int C, float eps, float momentum, float* mean, float* invstd,
                   float* running_mean, float* running_var, void* ws, void* stream);
+int tatt_bn_finalize(const void* acc, long long P, int C, float eps, float momentum, float* mean, float* invstd,
+                     float* running_mean, float* running_var, void* stream);
 int tatt_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
                        float* invstd, void* stream);
 int tatt_bn_apply_fwd(const float* X, float* Y, const float* mean, const float* invstd, const float* gamma,

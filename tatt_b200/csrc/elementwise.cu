@@ -158,18 +158,36 @@ __global__ void tanh_bwd_nchw_to_nhwc_kernel(const float* __restrict__ dout, con
   }
 }
 
+// Mask of element e: 16-bit lane (e & 7) of Philox4x32-10(counter e >> 3) >= round(p * 65536)  (8 elements per Philox
+// call; the keep probability is quantised to 1/65536 like the attention dropout of attn.cu).  The fused decoder-layer
+// kernel (tc6_declayer.cu:row_dropout) draws the same bits.
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p,
-                               const unsigned long long* __restrict__ rng, unsigned long long site) {
+                               const unsigned long long* __restrict__ rng, unsigned long long site, int vec) {
   const float scale = 1.f / (1.f - p);
+  const uint32_t thr = (uint32_t)(p * 65536.f + 0.5f);
   const unsigned long long seed = rng[0], offset = rng[1] * 65536ull + site;
-  long long n4 = (n + 3) >> 2;
-  GRID_STRIDE(i, n4) {
-    float4 u = philox_uniform4(seed, offset, (unsigned long long)i);
-    long long b = i << 2;
-    float uu[4] = {u.x, u.y, u.z, u.w};
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const long long n8 = (n + 7) >> 3;
+  GRID_STRIDE(i, n8) {
+    const uint4 r = philox4x32_10(key, make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), (uint32_t)offset,
+                                                  (uint32_t)(offset >> 32)));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    float m[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (b + k < n) y[b + k] = uu[k] >= p ? x[b + k] * scale : 0.f;
+    for (int k = 0; k < 4; ++k) {
+      m[2 * k] = (w[k] & 0xffffu) >= thr ? scale : 0.f;
+      m[2 * k + 1] = (w[k] >> 16) >= thr ? scale : 0.f;
+    }
+    const long long b = i << 3;
+    if (vec && b + 8 <= n) {
+      const float4 a = *reinterpret_cast<const float4*>(x + b), c = *reinterpret_cast<const float4*>(x + b + 4);
+      *reinterpret_cast<float4*>(y + b) = make_float4(a.x * m[0], a.y * m[1], a.z * m[2], a.w * m[3]);
+      *reinterpret_cast<float4*>(y + b + 4) = make_float4(c.x * m[4], c.y * m[5], c.z * m[6], c.w * m[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (b + k < n) y[b + k] = x[b + k] * m[k];
+    }
   }
 }
 
@@ -399,7 +417,8 @@ int tatt_dropout(const float* x, float* y, long long n, float p, const unsigned 
                  unsigned long long site, void* stream) {
   TATT_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
   if (n <= 0) return 0;
-  dropout_kernel<<<ew_blocks((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, rng, site);
+  const int vec = ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 ? 1 : 0;
+  dropout_kernel<<<ew_blocks((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, rng, site, vec);
   TATT_LAUNCH_CHECK("dropout_kernel");
   return 0;
 }

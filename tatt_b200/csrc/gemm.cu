@@ -709,7 +709,7 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
   if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout % 64 == 0 && Cout <= 256 && ws &&
       !(flags & (F_ACCUM | F_RELU | F_FP32))) {
     int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, Cout, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
-                                     ws_bytes, (cudaStream_t)stream);
+                                     ws_bytes, nullptr, (cudaStream_t)stream);
     if (rc >= 0) return rc;
   }
   GemmP p = {};
@@ -724,6 +724,28 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
   p.cH = H; p.cW = W; p.cC = Cin; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
   p.fdHW = make_fd(H * W); p.fdW = make_fd(W); p.fdC = make_fd(Cin); p.fdKW = make_fd(KW);
   return run_gemm(p, A_IM2COL, B_KN, false, (cudaStream_t)stream);
+}
+
+// 3x3 / 64 -> 64 convolution with the BatchNorm statistics of its output from the same pass: stats[0..63] += sum over
+// pixels of Y, stats[64..127] += sum of Y^2 (doubles, zeroed here).  Only the persistent TMA kernel does this: returns
+// an error when the shape is not served by it (W % 128, H % 2, workspace) -- tatt_conv3x3_stats_supported() tells.
+int tatt_conv3x3_stats_supported(int H, int W, int Cin, int Cout) {
+  static const bool off = []() {
+    const char* e = getenv("TATT_TMA");
+    return e && atoi(e) != 3;
+  }();
+  return (!off && Cin == 64 && Cout == 64 && W % 128 == 0 && H % 2 == 0) ? 1 : 0;
+}
+int tatt_conv3x3_stats(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W, int flags,
+                       void* ws, long long ws_bytes, void* stats, void* stream) {
+  TATT_REQUIRE(stats != nullptr && ws != nullptr && !(flags & (F_ACCUM | F_RELU | F_FP32)), "conv3x3_stats: bad arguments");
+  TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv3x3_stats: too many pixels");
+  cudaStream_t st = (cudaStream_t)stream;
+  TATT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 128, st));
+  int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, 64, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
+                                   ws_bytes, reinterpret_cast<double*>(stats), st);
+  if (rc < 0) return tatt_set_error("conv3x3_stats: shape [%d,%d,%d] is not served by the TMA kernel", nimg, H, W);
+  return rc;
 }
 
 // dWt[KH*KW*Cin][Cout] = im2col(X)^T * dY[nimg*H*W][Cout]   (zeroed here, split-K atomics)

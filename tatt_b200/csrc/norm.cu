@@ -336,6 +336,17 @@ int tatt_bn_stats(const float* X, long long P, int C, float eps, float momentum,
   return 0;
 }
 
+// mean / invstd (+ running-statistics update) from per-channel {sum, sum of squares} doubles produced elsewhere
+// (tatt_conv3x3_stats): the second half of tatt_bn_stats
+int tatt_bn_finalize(const void* acc, long long P, int C, float eps, float momentum, float* mean, float* invstd,
+                     float* running_mean, float* running_var, void* stream) {
+  TATT_REQUIRE(P >= 1 && C >= 1 && acc != nullptr, "bn_finalize: empty input");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>((const double*)acc, P, C, eps, momentum, mean,
+                                                                         invstd, running_mean, running_var);
+  TATT_LAUNCH_CHECK("bn_finalize_kernel");
+  return 0;
+}
+
 int tatt_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
                        float* invstd, void* stream) {
   bn_eval_stats_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, eps, C,

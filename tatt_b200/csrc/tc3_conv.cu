@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(192, 1)
 conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                     float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles, int dbg, int ldy,
-                    int ngroups) {
+                    int ngroups, double* __restrict__ stats) {
   // C_out = 64 * ngroups: work item w = g * ntiles + t is the 64-channel output group g of pixel tile t (the same halo
   // tile is re-read per group, mostly from L2; every group is the 64 -> 64 problem with its own weight slice)
   constexpr uint32_t acc_stride = cat ? 256u : 128u, row_stride = cat ? 128u : 64u;
@@ -463,10 +463,36 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     unsigned char* stg = stg_base + lg * (32 * 128);
     const int pq = lane >> 3, cc = lane & 7;          // copy-out: pixel 4 i + pq, float4 column cc of the 32-channel half
     float4 bb[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    // BatchNorm statistics of the output (stats != nullptr): per-channel sum and sum of squares of what is stored,
+    // accumulated per thread over its pixels (fixed 2 x 4 channels per lane), flushed per output-channel group
+    float4 ssum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)}, ssq[2] = {ssum[0], ssum[0]};
+    auto flush_stats = [&](int g) {
+      if (!stats || g < 0) return;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[8] = {ssum[h].x, ssum[h].y, ssum[h].z, ssum[h].w, ssq[h].x, ssq[h].y, ssq[h].z, ssq[h].w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
+          v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+        }
+        if (pq == 0) {
+          const int c0 = g * 64 + h * 32 + cc * 4, C = 64 * ngroups;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            atomicAdd(stats + c0 + k, (double)v[k]);
+            atomicAdd(stats + C + c0 + k, (double)v[4 + k]);
+          }
+        }
+        ssum[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ssq[h] = ssum[h];
+      }
+    };
     int it = 0, gcur = -1;
     for (int w = t0; w < t1; ++w, ++it) {
       const int g = w / ntiles, t = w - g * ntiles;
       if (g != gcur) {
+        flush_stats(gcur);
         gcur = g;
         if (bias) {
 #pragma unroll
@@ -506,6 +532,11 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             const int p = 4 * i + pq;
             float4 o = *reinterpret_cast<const float4*>(stg + p * 128 + ((cc ^ (p & 7)) << 4));
             o.x += bb[h].x; o.y += bb[h].y; o.z += bb[h].z; o.w += bb[h].w;
+            if (stats) {
+              ssum[h].x += o.x; ssum[h].y += o.y; ssum[h].z += o.z; ssum[h].w += o.w;
+              ssq[h].x = fmaf(o.x, o.x, ssq[h].x); ssq[h].y = fmaf(o.y, o.y, ssq[h].y);
+              ssq[h].z = fmaf(o.z, o.z, ssq[h].z); ssq[h].w = fmaf(o.w, o.w, ssq[h].w);
+            }
             if (!(dbg & 1)) *reinterpret_cast<float4*>(dst + (long long)(4 * i) * ldy + h * 32) = o;
           }
           __syncwarp();
@@ -515,6 +546,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[it & 1]));
     }
+    flush_stats(gcur);
   }
   tc_fence_before();
   __syncthreads();
@@ -703,13 +735,14 @@ static inline long long rup8(long long x) { return (x + 7) & ~7LL; }
 // conv3x3 64 -> Cout (64, 128, 192 or 256) through the TMA kernel.  Returns 0 ok, 1 error, -1 not eligible (caller
 // falls through).  Cout > 64 needs the persistent rolling-halo kernel (mode 3).
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
-                            int Cout, int single, int a_valid, void* ws, long long ws_bytes, cudaStream_t st) {
+                            int Cout, int single, int a_valid, void* ws, long long ws_bytes, double* stats,
+                            cudaStream_t st) {
   static const int mode = []() {          // TATT_TMA: 0 = off, 1 / 2 = one tile per CTA (base_offset 0 / from address),
     const char* e = getenv("TATT_TMA");   //           3 = persistent rolling-halo kernel (default)
     return e ? atoi(e) : 3;
   }();
   if (mode == 0 || ws == nullptr || W % TW != 0 || H % 2 != 0) return -1;
-  if (Cout % 64 != 0 || Cout < 64 || Cout > 256 || (Cout != 64 && mode != 3)) return -1;
+  if (Cout % 64 != 0 || Cout < 64 || Cout > 256 || ((Cout != 64 || stats) && mode != 3)) return -1;
   const int ngroups = Cout / 64;
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;
@@ -771,13 +804,16 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
     }();
     if (single) {
       TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<true, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups);
+      conv3x3_roll_kernel<true, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups,
+                                                             stats);
     } else if (cat_on) {
       TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<false, true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups);
+      conv3x3_roll_kernel<false, true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups,
+                                                             stats);
     } else {
       TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<false, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups);
+      conv3x3_roll_kernel<false, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups,
+                                                             stats);
     }
     TATT_LAUNCH_CHECK("conv3x3_roll_kernel");
     return 0;

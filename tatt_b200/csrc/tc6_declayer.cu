@@ -118,17 +118,24 @@ __device__ __forceinline__ void tmem_row64(uint32_t taddr, float (&row)[64]) {
   }
 }
 
-// the same mask as dropout_kernel (elementwise.cu): element e of the flat [P][64] tensor uses Philox counter e >> 2
+// the same mask as dropout_kernel (elementwise.cu): element e of the flat [P][64] tensor uses the 16-bit lane (e & 7) of
+// Philox counter e >> 3, i.e. 8 calls per token row
 __device__ __forceinline__ void row_dropout(float (&row)[64], float p, unsigned long long seed, unsigned long long offset,
                                             long long t) {
   const float scale = 1.f / (1.f - p);
+  const uint32_t thr = (uint32_t)(p * 65536.f + 0.5f);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
-  for (int c4 = 0; c4 < 16; ++c4) {
-    const float4 u = philox_uniform4(seed, offset, (unsigned long long)(t * 16 + c4));
-    row[c4 * 4 + 0] = u.x >= p ? row[c4 * 4 + 0] * scale : 0.f;
-    row[c4 * 4 + 1] = u.y >= p ? row[c4 * 4 + 1] * scale : 0.f;
-    row[c4 * 4 + 2] = u.z >= p ? row[c4 * 4 + 2] * scale : 0.f;
-    row[c4 * 4 + 3] = u.w >= p ? row[c4 * 4 + 3] * scale : 0.f;
+  for (int c8 = 0; c8 < 8; ++c8) {
+    const unsigned long long idx = (unsigned long long)(t * 8 + c8);
+    const uint4 r = philox4x32_10(key, make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset,
+                                                  (uint32_t)(offset >> 32)));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      row[c8 * 8 + 2 * k] *= (w[k] & 0xffffu) >= thr ? scale : 0.f;
+      row[c8 * 8 + 2 * k + 1] *= (w[k] >> 16) >= thr ? scale : 0.f;
+    }
   }
 }
 

@@ -422,10 +422,12 @@ def _conv_ws(x: Tensor, nx: int, ndy: int, extra: int):
 
 
 def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Optional[dict] = None,
-               relu: bool = False) -> Tensor:
+               relu: bool = False, stats: Optional[dict] = None) -> Tensor:
     """x [N,H,W,CinP] (CinP >= w.shape[1], multiple of 4) -> y [N,H,W,CoutP] (same H x W: out-of-image taps read 0).
     `keep` (a dict owned by the caller's tape entry) receives the workspace whose X planes the backward pass reuses;
-    `relu` fuses max(., 0) into the epilogue (generic engine only)."""
+    `relu` fuses max(., 0) into the epilogue (generic engine only); `stats` (a dict) receives under "acc" the
+    per-channel {sum, sum of squares} of y (2*Cout doubles) when the layer is served by the kernel that produces them
+    in its epilogue (tatt_conv3x3_stats) -- the BatchNorm that follows then skips its own statistics pass."""
     n, h, wd, cin_p = x.shape
     co, ci, kh, kw = w.shape
     cout_p = _pad4(co)
@@ -448,6 +450,17 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Option
             keep["ws"] = ws
         return y
     wt = conv_pack(w, cin_p, cout_p, False)
+    if (stats is not None and kh == 3 and kw == 3 and pad == 1 and not relu and not (_precision_flag & F_FP32)
+            and _cabi.lib().tatt_conv3x3_stats_supported(h, wd, cin_p, cout_p)):
+        ws = _conv_ws(x, x.numel(), P * _r8(cout_p),
+                      max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
+        acc = torch.empty(2 * cout_p, dtype=torch.float64, device=x.device)
+        _cabi.call("tatt_conv3x3_stats", _p(x), _p(wt), _p(b), _p(y), n, h, wd, _precision_flag, _p(ws), ws.numel(),
+                   _p(acc), _stream())
+        stats["acc"] = acc
+        if keep is not None:
+            keep["ws"] = ws
+        return y
     ws = _conv_ws(x, x.numel(), P * _r8(cout_p),
                   max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
     _cabi.call("tatt_conv2d_igemm", _p(x), _p(wt), _p(b), _p(y), n, h, wd, cin_p, cout_p, kh, kw, pad, pad,
@@ -558,6 +571,15 @@ def bn_stats(x2: Tensor, eps: float, momentum: float, running_mean: Optional[Ten
     ws = torch.empty(2 * C, dtype=torch.float64, device=x2.device)
     _cabi.call("tatt_bn_stats", _p(x2), P, C, eps, momentum, _p(st[0]), _p(st[1]), _p(running_mean),
                _p(running_var), _p(ws), _stream())
+    return st[0], st[1]
+
+
+def bn_finalize(acc: Tensor, P: int, C: int, eps: float, momentum: float, running_mean: Optional[Tensor],
+                running_var: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """mean / invstd from {sum, sum of squares} accumulated by the producing convolution (conv2d_fwd(stats=...))"""
+    st = torch.empty(2, C, dtype=torch.float32, device=acc.device)
+    _cabi.call("tatt_bn_finalize", _p(acc), P, C, eps, momentum, _p(st[0]), _p(st[1]), _p(running_mean), _p(running_var),
+               _stream())
     return st[0], st[1]
 
 

@@ -147,9 +147,9 @@ def srb_stage(blk: torch.nn.Module, x: Tensor, tp_map: Optional[Tensor], trainin
         if C != 64:
             raise NotImplementedError("tatt_b200 kernels are specialised for hidden_units=32 (64 channels)")
         tp4 = as_nhwc(t[1]) if tp_map is not None else None
-        r = tape.conv(x4, blk.conv1.weight, blk.conv1.bias, 1)
+        r = tape.conv(x4, blk.conv1.weight, blk.conv1.bias, 1, bn_next=training)
         r = tape.batchnorm(r, blk.bn1, ops.ACT_MISH, training)
-        r = tape.conv(r, blk.conv2.weight, blk.conv2.bias, 1)
+        r = tape.conv(r, blk.conv2.weight, blk.conv2.bias, 1, bn_next=training)
         r = tape.batchnorm(r, blk.bn2, ops.ACT_NONE, training)
         parts = [tape.view(r, -1, C)] + ([tape.view(tp4, -1, tp4.shape[-1])] if tp4 is not None else [])
         c1 = tape.linear_cat(parts, blk.gru1.conv1.weight, blk.gru1.conv1.bias)
@@ -377,7 +377,7 @@ def conv_bn_stage(seq: torch.nn.Sequential, x: Tensor, training: bool):
 
     def build(tape: Tape, t):
         x4 = as_nhwc(t[0])
-        y = tape.conv(x4, conv.weight, conv.bias, conv.padding[0])
+        y = tape.conv(x4, conv.weight, conv.bias, conv.padding[0], bn_next=(bn is not None and training))
         if bn is not None:
             y = tape.batchnorm(y, bn, ops.ACT_NONE, training)
         return [fmap_out(y)], [fmap_in(x4)] + [In(p) for p in ps]

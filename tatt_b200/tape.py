@@ -21,6 +21,7 @@ class Tape:
         self._ops: List = []
         self._g: Dict[int, Tensor] = {}
         self._keep: List[Tensor] = []
+        self._stats: Dict[int, tuple] = {}   # conv outputs whose BatchNorm sums were produced by the conv kernel itself
         self._side_keep: List = []    # tensors read by side-stream kernels: kept alive until the join (see backward())
         self._pflag = None            # inside precision_scope(flag): forward ops AND their backward closures run in that mode
 
@@ -176,9 +177,14 @@ class Tape:
         return y
 
     def conv(self, x4: Tensor, w: Tensor, b: Optional[Tensor], pad: int, need_dx: bool = True,
-             relu: bool = False) -> Tensor:
+             relu: bool = False, bn_next: bool = False) -> Tensor:
+        """bn_next: a train-mode BatchNorm consumes the output next -- let the convolution kernel accumulate its
+        statistics in the epilogue when it can (picked up by batchnorm() through self._stats)."""
         keep = {} if self.record else None       # workspace whose X planes the backward pass reuses
-        y = ops.conv2d_fwd(x4, w, b, pad, keep=keep, relu=relu)
+        st = {} if bn_next else None
+        y = ops.conv2d_fwd(x4, w, b, pad, keep=keep, relu=relu, stats=st)
+        if st:
+            self._stats[id(y)] = (y, st["acc"])
 
         def bwd():
             dy = self.grad(y)
@@ -207,8 +213,13 @@ class Tape:
                 # torch: cumulative moving average 1/num_batches_tracked (a host-side value; nothing on this path
                 # constructs such a BatchNorm, so it is not a device-resident / graph-safe quantity)
                 raise NotImplementedError("tatt_b200: BatchNorm(momentum=None) (cumulative average) is not supported")
-            mean, invstd = ops.bn_stats(x2, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
-                                        bn.running_mean if training else None, bn.running_var if training else None)
+            pre = self._stats.pop(id(x), None)
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            rm, rv = (bn.running_mean, bn.running_var) if training else (None, None)
+            if pre is not None and pre[0] is x and pre[1].numel() == 2 * C:
+                mean, invstd = ops.bn_finalize(pre[1], x2.shape[0], C, bn.eps, mom, rm, rv)
+            else:
+                mean, invstd = ops.bn_stats(x2, bn.eps, mom, rm, rv)
             if training and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked.add_(1)
         else:
