@@ -221,6 +221,8 @@ def step_profile(trainer, Trainer, xs, ts_, third, peaks, bf16):
     # kernels are timed one at a time: the side stream (weight gradients overlapping the data-gradient chain) is off for
     # this one step, otherwise concurrent kernels would stretch each other's event pairs
     side_was, ops._side_enabled = ops._side_enabled, False
+    # rank 0 profiles alone (the other ranks have left): no collective inside these two steps
+    world_was, trainer.world = trainer.world, 1
     Trainer.step(trainer, xs, ts_, third)                    # warm caches / workspaces on the eager path
     torch.cuda.synchronize()
     # An event pair brackets a HOST call: on an idle stream the first event fires at once and the pair then also counts the
@@ -233,6 +235,7 @@ def step_profile(trainer, Trainer, xs, ts_, third, peaks, bf16):
     with _cabi.Profile() as prof:
         Trainer.step(trainer, xs, ts_, third)
     ops._side_enabled = side_was
+    trainer.world = world_was
     del pad
     rows = prof.summary(lambda n, a: (n, entry_cost(n, a)[0]))
     total = sum(r[2] for r in rows)

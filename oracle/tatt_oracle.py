@@ -23,7 +23,7 @@ multi_head_attention_forward / layer_norm / grid_sample / pixel_shuffle); the or
 "those torch CPU ops in the reference's order" written as pure functions over a
 state_dict, so it is also a fair CPU baseline (same kernels the reference dispatches to).
 
-Pinning: `tests/test_oracle_vs_reference.py` checks this file against the live reference
+Pinning: `tests/test_oracle.py` checks this file against the live reference
 module (in the build container, where /root/reference exists) and against the committed
 fixtures in `tests/golden/` (everywhere).  The reference itself ships no golden vectors /
 tests, so parity is anchored on reference outputs generated here by

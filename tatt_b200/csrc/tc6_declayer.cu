@@ -52,22 +52,43 @@ struct DecLayerParams {
   int N, Lq, Lk, ntiles;
 };
 
+// The tile loop of this kernel is one straight line of code that every warp executes once per tile; fully inlined it was
+// 15.5 k SASS instructions (250 KB) against a 32 KB L1.5 instruction cache, and ncu showed "no instruction" as the top
+// stall reason (9.5 stall cycles per issued instruction, SM issue slots 12 % busy).  Everything that repeats is therefore
+// a real function call (Philox: 40 calls per token row; the coalesced half of the row load / store helpers) or a rolled
+// loop (the four heads), so the body that streams from L2 is ~3x smaller and the callees stay cache-resident.
+__device__ __noinline__ uint4 philox_call(uint2 key, uint4 ctr) { return philox4x32_10(key, ctr); }
+
 __device__ __forceinline__ uint32_t sw128(int r, int k) {   // byte offset of bf16 element (r, k) in a K-major SW128 tile
   return (uint32_t)(r * 128 + ((((k >> 3) ^ (r & 7)) << 4) | ((k & 7) << 1)));
 }
 
 // warp-cooperative [32 rows][64] fp32 <-> one row per lane, through a warp-private 4 KB swizzled staging buffer
-// (coalesced 128-byte global segments; conflict-free shared-memory accesses)
+// (coalesced 128-byte global segments; conflict-free shared-memory accesses).  The global <-> staging halves are real
+// calls (see the note on code size above); the register <-> staging halves must stay inline (register arrays).
+__device__ __noinline__ void stage_in(const float* __restrict__ g, unsigned char* stg, int lane) {   // 32 rows x 32 floats
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = i * 32 + lane, r = f >> 3, c = f & 7;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g + (long long)r * 64 + c * 4));
+    *reinterpret_cast<float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+  __syncwarp();
+}
+__device__ __noinline__ void stage_out(float* __restrict__ g, const unsigned char* stg, int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = i * 32 + lane, r = f >> 3, c = f & 7;
+    *reinterpret_cast<float4*>(g + (long long)r * 64 + c * 4) =
+        *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void load_rows(const float* __restrict__ g, float (&row)[64], unsigned char* stg, int lane) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int f = i * 32 + lane, r = f >> 3, c = f & 7;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(g + (long long)r * 64 + h * 32 + c * 4));
-      *reinterpret_cast<float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4)) = v;
-    }
-    __syncwarp();
+    stage_in(g + h * 32, stg, lane);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float4 v = *reinterpret_cast<const float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4));
@@ -83,14 +104,7 @@ __device__ __forceinline__ void store_rows(float* __restrict__ g, const float (&
     for (int c = 0; c < 8; ++c)
       *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
           make_float4(row[h * 32 + c * 4], row[h * 32 + c * 4 + 1], row[h * 32 + c * 4 + 2], row[h * 32 + c * 4 + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int f = i * 32 + lane, r = f >> 3, c = f & 7;
-      *reinterpret_cast<float4*>(g + (long long)r * 64 + h * 32 + c * 4) =
-          *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
-    }
-    __syncwarp();
+    stage_out(g + h * 32, stg, lane);
   }
 }
 
@@ -128,8 +142,8 @@ __device__ __forceinline__ void row_dropout(float (&row)[64], float p, unsigned 
 #pragma unroll
   for (int c8 = 0; c8 < 8; ++c8) {
     const unsigned long long idx = (unsigned long long)(t * 8 + c8);
-    const uint4 r = philox4x32_10(key, make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset,
-                                                  (uint32_t)(offset >> 32)));
+    const uint4 r = philox_call(key, make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset,
+                                                (uint32_t)(offset >> 32)));
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -318,9 +332,9 @@ __global__ void __launch_bounds__(DL_THREADS, 1) tp_declayer_fwd_kernel(const De
     float aw[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) aw[j] = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int rd = 0; rd < 2; ++rd) {
-#pragma unroll
+#pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
         const int h = 2 * rd + hh;
         float s[32];
@@ -360,8 +374,8 @@ __global__ void __launch_bounds__(DL_THREADS, 1) tp_declayer_fwd_kernel(const De
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             const unsigned long long idx = (unsigned long long)(elem * 4 + j8);
-            const uint4 rr = philox4x32_10(key, make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset,
-                                                           (uint32_t)(offset >> 32)));
+            const uint4 rr = philox_call(key, make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset,
+                                                         (uint32_t)(offset >> 32)));
             const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
