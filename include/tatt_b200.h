@@ -219,6 +219,9 @@ int tatt_tps_sample_bwd(const float* X, const float* ctrl, const float* invK, co
 
 /* ---- gradient step on a flat buffer: clip_grad_norm_(0.25) + Adam, interfaces/super_resolution.py:1083-1085 */
 int tatt_sqnorm(const float* x, long long n, float* out, int zero_first, void* stream);
+/* the same sum with a fixed reduction order (per-block partials in ws[ws_floats], then one block): bit-identical on every
+ * data-parallel replica, which all clip the same all-reduced gradient */
+int tatt_sqnorm_det(const float* x, long long n, float* out, float* ws, int ws_floats, void* stream);
 /* gradient packing in one launch: table = DEVICE array of nchunks x {source address, destination offset (floats),
  * count (floats, <= 16384)}; sq (optional) receives sum(x^2) over everything copied (zeroed first) */
 int tatt_multi_copy(const unsigned long long* table, int nchunks, float* dst, float* sq, void* stream);

@@ -11,7 +11,7 @@ from typing import Dict, List, Tuple
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(HERE, "..", "include", "tatt_b200.h")
-LIB_PATH = os.path.join(HERE, "lib", "libtatt_b200.so")
+LIB_PATH = os.environ.get("TATT_LIB") or os.path.join(HERE, "lib", "libtatt_b200.so")   # TATT_LIB: kernel-variant experiments
 
 _CTYPES = {
     "int": ctypes.c_int,

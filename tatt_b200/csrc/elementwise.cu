@@ -259,6 +259,35 @@ __global__ void sqnorm_kernel(const float* __restrict__ x, long long n, float* _
   }
 }
 
+// Deterministic variant (fixed reduction order, no atomics): data-parallel replicas must derive the SAME clip coefficient
+// from the same all-reduced gradient, bit for bit, or they drift apart by an ulp per step.
+__global__ void sqnorm_partial_kernel(const float* __restrict__ x, long long n, float* __restrict__ part) {
+  __shared__ float red[8];
+  float s = 0.f;
+  GRID_STRIDE(i, n) s = fmaf(x[i], x[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void sqnorm_final_kernel(const float* __restrict__ part, int nparts, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 256) s += part[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    out[0] = t;
+  }
+}
+
 // Gradient packing as ONE launch: chunk c copies tab[3c+2] floats from address tab[3c] to dst + tab[3c+1]
 // (chunks are <= 16384 floats; 16-byte aligned sources take the float4 path) and, when sq != nullptr, adds the
 // chunk's sum of squares to sq[0] (the global-norm numerator of clip_grad_norm_ for a single-rank step).
@@ -459,6 +488,22 @@ int tatt_sqnorm(const float* x, long long n, float* out, int zero_first, void* s
   if (n <= 0) return 0;
   sqnorm_kernel<<<ew_blocks(n, 2048), 256, 0, st>>>(x, n, out);
   TATT_LAUNCH_CHECK("sqnorm_kernel");
+  return 0;
+}
+
+int tatt_sqnorm_det(const float* x, long long n, float* out, float* ws, int ws_floats, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TATT_REQUIRE(ws != nullptr && ws_floats >= 1, "sqnorm_det: needs a scratch buffer");
+  if (n <= 0) {
+    TATT_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+    return 0;
+  }
+  int nb = ew_blocks(n, 2048);
+  if (nb > ws_floats) nb = ws_floats;
+  sqnorm_partial_kernel<<<nb, 256, 0, st>>>(x, n, ws);
+  TATT_LAUNCH_CHECK("sqnorm_partial_kernel");
+  sqnorm_final_kernel<<<1, 256, 0, st>>>(ws, nb, out);
+  TATT_LAUNCH_CHECK("sqnorm_final_kernel");
   return 0;
 }
 

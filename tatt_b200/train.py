@@ -176,7 +176,10 @@ class Trainer:
                 raise RuntimeError("a parameter was re-assigned after the Trainer flattened it (model.to()/.float()/"
                                    "load with assign=True?); rebuild the Trainer")
         if self.world > 1:
-            _cabi.call("tatt_sqnorm", g.data_ptr(), b.numel, self.sq.data_ptr(), 1, st)
+            # deterministic reduction: every replica must clip with the bit-identical norm of the all-reduced gradient
+            if getattr(self, "_sq_ws", None) is None:
+                self._sq_ws = torch.empty(1024, dtype=torch.float32, device=g.device)
+            _cabi.call("tatt_sqnorm_det", g.data_ptr(), b.numel, self.sq.data_ptr(), self._sq_ws.data_ptr(), 1024, st)
         _cabi.call("tatt_rng_advance", self.step_state.data_ptr(), st)
         _cabi.call("tatt_adam_clip_step", b.flat_param.data_ptr(), g.data_ptr(), self.m.data_ptr(),
                    self.v.data_ptr(), b.numel, self.sq.data_ptr(), self.max_norm, self.lr, self.betas[0],
