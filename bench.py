@@ -34,7 +34,7 @@ ALG_FLOPS_FWD_BWD_G32 = 3.0 * 9.33e9     # ~9.33 GFLOP/img forward (R
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
