@@ -190,6 +190,9 @@ def entry_cost(name, a):
         n, H, W, Ci, Co, KH, KW = a[4:11]
         return ("%dx%d %d->%d" % (KH, KW, Ci, Co), 2.0 * n * H * W * Co * KH * KW * Ci,
                 f * n * H * W * (Ci + Co), "tensor")
+    if name == "tatt_conv3x3_stats":          # 3x3 64 -> 64 forward + BatchNorm sums in the epilogue
+        n, H, W = a[4:7]
+        return "3x3 64->64", 2.0 * n * H * W * 64 * 576, f * n * H * W * 128, "tensor"
     if name == "tatt_conv2d_wgrad":
         n, H, W, Ci, Co, KH, KW = a[3:10]
         return ("%dx%d %d->%d" % (KH, KW, Ci, Co), 2.0 * n * H * W * Co * KH * KW * Ci,
@@ -238,6 +241,31 @@ def step_profile(trainer, Trainer, xs, ts_, third, peaks, bf16):
     trainer.world = world_was
     del pad
     rows = prof.summary(lambda n, a: (n, entry_cost(n, a)[0]))
+    # Second pass over the largest groups: loops of many short calls (the 63 RPE backward steps: two launches + four event
+    # records per ~25 us of device work) are HOST-bound in eager mode even with the backlog, so their pairs still contain
+    # launch latency.  The first recorded call of each of the 16 largest groups is therefore re-issued 8 times back to
+    # back inside ONE event pair (same arguments; the buffers are free blocks of the caching allocator by now, still
+    # mapped -- the results are garbage and nothing reads them) and the group's time becomes calls x that average.
+    # Entries with persistent side effects are left as measured.
+    keep_eager = {"tatt_adam_clip_step", "tatt_rng_advance", "tatt_bn_stats", "tatt_bn_finalize", "tatt_memcpy_d2d",
+                  "tatt_memset0", "tatt_multi_copy"}
+    L = _cabi.lib()
+    retimed = {}
+    for (n, key), calls, tsum, _, args in rows[:16]:
+        if n in keep_eager:
+            continue
+        fn = getattr(L, n)
+        if fn(*args) != 0:
+            continue
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(8):
+            fn(*args)
+        r1.record()
+        torch.cuda.synchronize()
+        retimed[(n, key)] = r0.elapsed_time(r1) * 1e-3 / 8
+    rows = sorted(((k, c, (retimed[k] * c if k in retimed else t), n_, a) for k, c, t, n_, a in rows), key=lambda r: -r[2])
     total = sum(r[2] for r in rows)
     tpk = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
     hpk = peaks.get("hbm_gbs", 6450.0)
@@ -245,7 +273,8 @@ def step_profile(trainer, Trainer, xs, ts_, third, peaks, bf16):
     for (n, key), calls, tsum, _, args in rows[:10]:
         _, fl, by, bound = entry_cost(n, args)
         avg = tsum / calls
-        e = {"entry": n, "shape": key, "calls": calls, "share": tsum / total, "avg_us": avg * 1e6, "bound": bound}
+        e = {"entry": n, "shape": key, "calls": calls, "share": tsum / total, "avg_us": avg * 1e6, "bound": bound,
+             "timed": "8 back-to-back re-issues in one event pair" if (n, key) in retimed else "event pair per call"}
         if fl:
             e["tflops"] = fl / avg / 1e12
             e["tensor_frac"] = e["tflops"] / tpk

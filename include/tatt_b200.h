@@ -93,9 +93,11 @@ int tatt_conv2d_wgrad(const float* X, const float* dY, float* dWt, int nimg, int
                       int KH, int KW, int padH, int padW, int flags, void* ws, long long ws_bytes, void* stream);
 
 /* 3x3 / 64 -> 64 convolution (tsrn.py:876,884,611) that also yields the BatchNorm statistics of its output from the same
- * pass: stats = 128 doubles {sum_c, sumsq_c} (zeroed here, fp32 partials per thread -> fp64 atomics in the epilogue of the
- * persistent TMA kernel); tatt_bn_finalize turns them into mean / invstd (+ running statistics).  Served shapes only
- * (tatt_conv3x3_stats_supported != 0: W % 128 == 0, H % 2 == 0); flags 1024 / 2048 as for tatt_conv2d_igemm. */
+ * pass: stats = TATT_CONV_STATS_ROWS rows of 128 floats, row c = {sum_ch[64], sumsq_ch[64]} over the pixels CTA c of the
+ * persistent TMA kernel stored (zeroed here; no atomics); tatt_bn_finalize(nparts = TATT_CONV_STATS_ROWS) adds the rows in
+ * double and produces mean / invstd (+ running statistics).  Served shapes only (tatt_conv3x3_stats_supported != 0:
+ * W % 128 == 0, H % 2 == 0); flags 1024 / 2048 as for tatt_conv2d_igemm. */
+#define TATT_CONV_STATS_ROWS 160
 int tatt_conv3x3_stats_supported(int H, int W, int Cin, int Cout);
 int tatt_conv3x3_stats(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W, int flags,
                        void* ws, long long ws_bytes, void* stats, void* stream);
@@ -116,8 +118,9 @@ int tatt_conv_kxexp_expand(const float* dOut, float* dT, long long P, int W, int
  * (model/tsrn.py:1061-1064).  ws: scratch of >= 2*C doubles. */
 int tatt_bn_stats(const float* X, long long P, int C, float eps, float momentum, float* mean, float* invstd,
                   float* running_mean, float* running_var, void* ws, void* stream);
-int tatt_bn_finalize(const void* acc, long long P, int C, float eps, float momentum, float* mean, float* invstd,
-                     float* running_mean, float* running_var, void* stream);
+/* parts: nparts rows of {sum[C], sumsq[C]} floats (per-CTA partial sums of a producing kernel), added in double */
+int tatt_bn_finalize(const float* parts, int nparts, long long P, int C, float eps, float momentum, float* mean,
+                     float* invstd, float* running_mean, float* running_var, void* stream);
 int tatt_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
                        float* invstd, void* stream);
 int tatt_bn_apply_fwd(const float* X, float* Y, const float* mean, const float* invstd, const float* gamma,

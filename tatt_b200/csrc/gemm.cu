@@ -726,9 +726,10 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
   return run_gemm(p, A_IM2COL, B_KN, false, (cudaStream_t)stream);
 }
 
-// 3x3 / 64 -> 64 convolution with the BatchNorm statistics of its output from the same pass: stats[0..63] += sum over
-// pixels of Y, stats[64..127] += sum of Y^2 (doubles, zeroed here).  Only the persistent TMA kernel does this: returns
-// an error when the shape is not served by it (W % 128, H % 2, workspace) -- tatt_conv3x3_stats_supported() tells.
+// 3x3 / 64 -> 64 convolution with the BatchNorm statistics of its output from the same pass: stats[c][0..63] = sum over
+// the pixels CTA c stored, stats[c][64..127] = sum of squares (TATT_CONV_STATS_ROWS rows of 128 floats, zeroed here; rows
+// of CTAs that do not exist stay zero).  Only the persistent TMA kernel does this: returns an error when the shape is not
+// served by it (W % 128, H % 2, workspace) -- tatt_conv3x3_stats_supported() tells.
 int tatt_conv3x3_stats_supported(int H, int W, int Cin, int Cout) {
   static const bool off = []() {
     const char* e = getenv("TATT_TMA");
@@ -741,9 +742,12 @@ int tatt_conv3x3_stats(const float* X, const float* Wt, const float* bias, float
   TATT_REQUIRE(stats != nullptr && ws != nullptr && !(flags & (F_ACCUM | F_RELU | F_FP32)), "conv3x3_stats: bad arguments");
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv3x3_stats: too many pixels");
   cudaStream_t st = (cudaStream_t)stream;
-  TATT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 128, st));
+  TATT_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 128 * TATT_CONV_STATS_ROWS, st));
+  int dev = 0, nsm = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  TATT_REQUIRE(nsm <= TATT_CONV_STATS_ROWS, "conv3x3_stats: device has more SMs (%d) than statistics rows", nsm);
   int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, 64, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
-                                   ws_bytes, reinterpret_cast<double*>(stats), st);
+                                   ws_bytes, reinterpret_cast<float*>(stats), st);
   if (rc < 0) return tatt_set_error("conv3x3_stats: shape [%d,%d,%d] is not served by the TMA kernel", nimg, H, W);
   return rc;
 }

@@ -61,7 +61,7 @@ int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* w
 
 // TMA + halo-reuse kernel for the 3x3 / 64->64 convolution (tc3_conv.cu); same return convention
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
-                            int Cout, int single, int a_valid, void* ws, long long ws_bytes, double* stats,
+                            int Cout, int single, int a_valid, void* ws, long long ws_bytes, float* stats,
                             cudaStream_t st);
 int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cout,
                                   int single, int a_valid, int b_valid, void* ws, long long ws_bytes, cudaStream_t st);

@@ -308,6 +308,30 @@ static int ew_blocks(long long n, int per = 256) {
   return (int)b;
 }
 
+// mean / invstd (+ running-statistics update) from per-CTA partial {sum, sum of squares} rows produced by the convolution
+// kernel's epilogue (tatt_conv3x3_stats): the rows are added in double in a fixed order
+__global__ void bn_finalize_parts_kernel(const float* __restrict__ parts, int nparts, long long P, int C, float eps,
+                                         float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < nparts; ++i) {
+    s += (double)parts[(long long)i * 2 * C + c];
+    q += (double)parts[(long long)i * 2 * C + C + c];
+  }
+  const double m = s / (double)P;
+  double var = q / (double)P - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -336,14 +360,12 @@ int tatt_bn_stats(const float* X, long long P, int C, float eps, float momentum,
   return 0;
 }
 
-// mean / invstd (+ running-statistics update) from per-channel {sum, sum of squares} doubles produced elsewhere
-// (tatt_conv3x3_stats): the second half of tatt_bn_stats
-int tatt_bn_finalize(const void* acc, long long P, int C, float eps, float momentum, float* mean, float* invstd,
-                     float* running_mean, float* running_var, void* stream) {
-  TATT_REQUIRE(P >= 1 && C >= 1 && acc != nullptr, "bn_finalize: empty input");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>((const double*)acc, P, C, eps, momentum, mean,
-                                                                         invstd, running_mean, running_var);
-  TATT_LAUNCH_CHECK("bn_finalize_kernel");
+int tatt_bn_finalize(const float* parts, int nparts, long long P, int C, float eps, float momentum, float* mean,
+                     float* invstd, float* running_mean, float* running_var, void* stream) {
+  TATT_REQUIRE(P >= 1 && C >= 1 && nparts >= 1 && parts != nullptr, "bn_finalize: empty input");
+  bn_finalize_parts_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(parts, nparts, P, C, eps, momentum, mean, invstd,
+                                                                           running_mean, running_var);
+  TATT_LAUNCH_CHECK("bn_finalize_parts_kernel");
   return 0;
 }
 

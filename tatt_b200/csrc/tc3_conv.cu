@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(192, 1)
 conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                     float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles, int dbg, int ldy,
-                    int ngroups, double* __restrict__ stats) {
+                    int ngroups, float* __restrict__ stats) {
   // C_out = 64 * ngroups: work item w = g * ntiles + t is the 64-channel output group g of pixel tile t (the same halo
   // tile is re-read per group, mostly from L2; every group is the 64 -> 64 problem with its own weight slice)
   constexpr uint32_t acc_stride = cat ? 256u : 128u, row_stride = cat ? 128u : 64u;
@@ -302,6 +302,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   __shared__ __align__(8) unsigned long long pair_full[2], pair_empty[2], w_full[RL_NSTAGE], w_empty[RL_NSTAGE], acc_full[2],
       acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float stat_red[4 * 128];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nyb = H / 2, nxt = W / TW;
   const int t0 = (int)((long long)blockIdx.x * ntiles * ngroups / gridDim.x);
@@ -463,11 +464,15 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     unsigned char* stg = stg_base + lg * (32 * 128);
     const int pq = lane >> 3, cc = lane & 7;          // copy-out: pixel 4 i + pq, float4 column cc of the 32-channel half
     float4 bb[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-    // BatchNorm statistics of the output (stats != nullptr): per-channel sum and sum of squares of what is stored,
-    // accumulated per thread over its pixels (fixed 2 x 4 channels per lane), flushed per output-channel group
+    // BatchNorm statistics of the output (stats != nullptr, one output-channel group): per-channel sum and sum of
+    // squares of what is stored, accumulated per thread over its pixels (fixed 2 x 4 channels per lane), reduced over
+    // the CTA in shared memory and written as ONE row of 128 floats per CTA (stats[blockIdx.x][{sum, sumsq}][64]);
+    // tatt_bn_finalize adds the rows in double.  (A first version used fp64 atomics on the 128 addresses straight from
+    // every warp: 75 k atomics on 128 addresses cost as much as the separate statistics pass it replaced.)
     float4 ssum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)}, ssq[2] = {ssum[0], ssum[0]};
     auto flush_stats = [&](int g) {
       if (!stats || g < 0) return;
+      float* red = reinterpret_cast<float*>(stat_red);          // [4 warps][128]
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float v[8] = {ssum[h].x, ssum[h].y, ssum[h].z, ssum[h].w, ssq[h].x, ssq[h].y, ssq[h].z, ssq[h].w};
@@ -477,16 +482,17 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
         }
         if (pq == 0) {
-          const int c0 = g * 64 + h * 32 + cc * 4, C = 64 * ngroups;
+          const int c0 = h * 32 + cc * 4;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            atomicAdd(stats + c0 + k, (double)v[k]);
-            atomicAdd(stats + C + c0 + k, (double)v[4 + k]);
+            red[lg * 128 + c0 + k] = v[k];
+            red[lg * 128 + 64 + c0 + k] = v[4 + k];
           }
         }
-        ssum[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ssq[h] = ssum[h];
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps
+      const int i = lg * 32 + lane;                               // 0..127
+      stats[(long long)blockIdx.x * 128 + i] = red[i] + red[128 + i] + red[256 + i] + red[384 + i];
     };
     int it = 0, gcur = -1;
     for (int w = t0; w < t1; ++w, ++it) {
@@ -735,14 +741,14 @@ static inline long long rup8(long long x) { return (x + 7) & ~7LL; }
 // conv3x3 64 -> Cout (64, 128, 192 or 256) through the TMA kernel.  Returns 0 ok, 1 error, -1 not eligible (caller
 // falls through).  Cout > 64 needs the persistent rolling-halo kernel (mode 3).
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
-                            int Cout, int single, int a_valid, void* ws, long long ws_bytes, double* stats,
+                            int Cout, int single, int a_valid, void* ws, long long ws_bytes, float* stats,
                             cudaStream_t st) {
   static const int mode = []() {          // TATT_TMA: 0 = off, 1 / 2 = one tile per CTA (base_offset 0 / from address),
     const char* e = getenv("TATT_TMA");   //           3 = persistent rolling-halo kernel (default)
     return e ? atoi(e) : 3;
   }();
   if (mode == 0 || ws == nullptr || W % TW != 0 || H % 2 != 0) return -1;
-  if (Cout % 64 != 0 || Cout < 64 || Cout > 256 || ((Cout != 64 || stats) && mode != 3)) return -1;
+  if (Cout % 64 != 0 || Cout < 64 || Cout > 256 || ((Cout != 64 || stats) && mode != 3) || (stats && Cout != 64)) return -1;
   const int ngroups = Cout / 64;
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;

@@ -454,7 +454,7 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Option
             and _cabi.lib().tatt_conv3x3_stats_supported(h, wd, cin_p, cout_p)):
         ws = _conv_ws(x, x.numel(), P * _r8(cout_p),
                       max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
-        acc = torch.empty(2 * cout_p, dtype=torch.float64, device=x.device)
+        acc = torch.empty(CONV_STATS_ROWS, 2 * cout_p, dtype=torch.float32, device=x.device)   # one row per CTA
         _cabi.call("tatt_conv3x3_stats", _p(x), _p(wt), _p(b), _p(y), n, h, wd, _precision_flag, _p(ws), ws.numel(),
                    _p(acc), _stream())
         stats["acc"] = acc
@@ -471,6 +471,7 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Option
 
 
 F_B_VALID = 4096
+CONV_STATS_ROWS = 160      # TATT_CONV_STATS_ROWS of include/tatt_b200.h
 
 
 class _NoSide:
@@ -578,8 +579,8 @@ def bn_finalize(acc: Tensor, P: int, C: int, eps: float, momentum: float, runnin
                 running_var: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
     """mean / invstd from {sum, sum of squares} accumulated by the producing convolution (conv2d_fwd(stats=...))"""
     st = torch.empty(2, C, dtype=torch.float32, device=acc.device)
-    _cabi.call("tatt_bn_finalize", _p(acc), P, C, eps, momentum, _p(st[0]), _p(st[1]), _p(running_mean), _p(running_var),
-               _stream())
+    _cabi.call("tatt_bn_finalize", _p(acc), acc.shape[0], P, C, eps, momentum, _p(st[0]), _p(st[1]), _p(running_mean),
+               _p(running_var), _stream())
     return st[0], st[1]
 
 

@@ -230,7 +230,9 @@ def rpe_stage(init_factor: torch.nn.Embedding, gru: torch.nn.GRU, N: int, H: int
                        None if GATES is None else GATES.data_ptr(), QPOS.data_ptr(),
                        HP.t.data_ptr() if fast else None, HP.lo_off if fast else 0, s, N, Wd, Hd, C, H, st())
         if fast:
-            del HP, WP
+            del WP
+            if not tape.record:
+                del HP                     # training keeps the hidden-state planes: B operand of the dW_hh GEMM
 
         def bwd():
             dQ = tape.grad(QPOS)
@@ -256,8 +258,15 @@ def rpe_stage(init_factor: torch.nn.Embedding, gru: torch.nn.GRU, N: int, H: int
                     ops.gemm(0, 0, DGH[0, s], 3 * Hd, WHH, Hd, DH, Hd, None, Wd, Hd, 3 * Hd, ops.F_ACCUM, batch=2,
                              sA=N * Wd * 3 * Hd, sB=3 * Hd * Hd, sC=Wd * Hd)
             dWHH = ops.empty(2, 3 * Hd, Hd, like=emb)
-            ops.gemm(1, 0, DGH, 3 * Hd, HALL, Hd, dWHH, Hd, None, 3 * Hd, Hd, N * Wd, ops.F_SPLITK | ops.F_ZEROC,
-                     batch=2, sA=N * Wd * 3 * Hd, sB=sH, sC=3 * Hd * Hd)
+            if fast:
+                # dW_hh = sum_s dgh_s^T h_{s-1}: both operands already exist as bf16 planes (dgh: written by the gate
+                # kernel for the chain GEMMs; h: written by the forward pass) -- no split passes over 270 MB
+                ops.gemm(1, 0, DP.t[0], 3 * Hd, HP.t[0], Hd, dWHH, Hd, None, 3 * Hd, Hd, N * Wd,
+                         ops.F_SPLITK | ops.F_ZEROC | ops.F_APLANES | ops.F_BPLANES, batch=2, sA=N * Wd * 3 * Hd, sB=sH,
+                         sC=3 * Hd * Hd, loA=DP.lo_off, loB=HP.lo_off)
+            else:
+                ops.gemm(1, 0, DGH, 3 * Hd, HALL, Hd, dWHH, Hd, None, 3 * Hd, Hd, N * Wd, ops.F_SPLITK | ops.F_ZEROC,
+                         batch=2, sA=N * Wd * 3 * Hd, sB=sH, sC=3 * Hd * Hd)
             dX = None
             for d in range(2):
                 tape.add_grad(w_hh[d], dWHH[d])

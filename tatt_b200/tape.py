@@ -216,7 +216,7 @@ class Tape:
             pre = self._stats.pop(id(x), None)
             mom = bn.momentum if bn.momentum is not None else 0.1
             rm, rv = (bn.running_mean, bn.running_var) if training else (None, None)
-            if pre is not None and pre[0] is x and pre[1].numel() == 2 * C:
+            if pre is not None and pre[0] is x and pre[1].shape[1] == 2 * C:
                 mean, invstd = ops.bn_finalize(pre[1], x2.shape[0], C, bn.eps, mom, rm, rv)
             else:
                 mean, invstd = ops.bn_stats(x2, bn.eps, mom, rm, rv)
