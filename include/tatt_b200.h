@@ -128,6 +128,12 @@ int tatt_bn_apply_fwd(const float* X, float* Y, const float* mean, const float* 
 int tatt_bn_bwd(const float* X, const float* dY, const float* mean, const float* invstd, const float* gamma,
                 const float* beta, int act, int training, long long P, int C, float* dX, float* dgamma,
                 float* dbeta, void* ws, void* stream);
+/* the same backward with dX written only as bf16 hi / lo planes [P][C] (operand format of the tcgen05 convolution kernels):
+ * the BatchNorm behind a 3x3 convolution hands that convolution's backward passes their dY planes (flag 4096 of
+ * tatt_conv2d_wgrad, flag 2048 of the data-gradient tatt_conv2d_igemm) -- no fp32 copy, no split pass */
+int tatt_bn_bwd_planes(const float* X, const float* dY, const float* mean, const float* invstd, const float* gamma,
+                       const float* beta, int act, int training, long long P, int C, void* dx_hi, void* dx_lo,
+                       float* dgamma, float* dbeta, void* ws, void* stream);
 
 /* ---- LayerNorm(64) with fused residual add: model/transformer_v2.py:460-461,792-794,166 -------------- */
 int tatt_layernorm64_fwd(const float* X, const float* R, const float* gamma, const float* beta, float* Y, float* S,

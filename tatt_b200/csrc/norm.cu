@@ -1,6 +1,7 @@
 // BatchNorm (channels-last, batch statistics over all rows) and LayerNorm(64) kernels, fwd + bwd.
 // Reference ops replaced: nn.BatchNorm2d/1d (model/tsrn.py:878,886,612; model/stn_head.py:19,51)
 // and nn.LayerNorm(64) (model/transformer_v2.py:460-461, 792-794, 166).
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -201,7 +202,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ X, const float* __
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, int act,
-                                    int training, float invP, long long total4, int C4, float* __restrict__ dX) {
+                                    int training, float invP, long long total4, int C4, float* __restrict__ dX,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
@@ -225,7 +227,15 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ X, const float* __
       if (act != ACT_NONE) dz *= act_grad(xh * gav[j] + bev[j], act);
       o[j] = training ? gav[j] * iv[j] * (dz - dbv[j] * invP - xh * dgv[j] * invP) : gav[j] * iv[j] * dz;
     }
-    reinterpret_cast<float4*>(dX)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (hi) {           // bf16 hi / lo operand planes of dX for the convolution in front (no fp32 copy, no split pass)
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(o[0] - f0.x, o[1] - f0.y), l1 = __floats2bfloat162_rn(o[2] - f1.x, o[3] - f1.y);
+      reinterpret_cast<uint2*>(hi)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      reinterpret_cast<uint2*>(lo)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    } else {
+      reinterpret_cast<float4*>(dX)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -389,9 +399,26 @@ int tatt_bn_apply_fwd(const float* X, float* Y, const float* mean, const float* 
 }
 
 // dgamma/dbeta (with the activation's backward fused) then dX.  ws: >= 2*C doubles.
+static int bn_bwd_impl(const float* X, const float* dY, const float* mean, const float* invstd, const float* gamma,
+                       const float* beta, int act, int training, long long P, int C, float* dX, void* dx_hi, void* dx_lo,
+                       float* dgamma, float* dbeta, void* ws, void* stream);
 int tatt_bn_bwd(const float* X, const float* dY, const float* mean, const float* invstd, const float* gamma,
                 const float* beta, int act, int training, long long P, int C, float* dX, float* dgamma,
                 float* dbeta, void* ws, void* stream) {
+  return bn_bwd_impl(X, dY, mean, invstd, gamma, beta, act, training, P, C, dX, nullptr, nullptr, dgamma, dbeta, ws, stream);
+}
+// The same backward, with dX written ONLY as bf16 hi / lo planes [P][C] (the operand format of the tcgen05 convolution
+// kernels): the BatchNorm behind a convolution hands the conv's backward passes their dY operand directly.
+int tatt_bn_bwd_planes(const float* X, const float* dY, const float* mean, const float* invstd, const float* gamma,
+                       const float* beta, int act, int training, long long P, int C, void* dx_hi, void* dx_lo,
+                       float* dgamma, float* dbeta, void* ws, void* stream) {
+  TATT_REQUIRE(dx_hi && dx_lo && C % 4 == 0 && ((((uintptr_t)dx_hi) | ((uintptr_t)dx_lo)) & 7) == 0,
+               "bn_bwd_planes: planes must be given, 8-byte aligned, C %% 4 == 0");
+  return bn_bwd_impl(X, dY, mean, invstd, gamma, beta, act, training, P, C, nullptr, dx_hi, dx_lo, dgamma, dbeta, ws, stream);
+}
+static int bn_bwd_impl(const float* X, const float* dY, const float* mean, const float* invstd, const float* gamma,
+                       const float* beta, int act, int training, long long P, int C, float* dX, void* dx_hi, void* dx_lo,
+                       float* dgamma, float* dbeta, void* ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   TATT_REQUIRE(P >= 1 && C >= 1, "bn_bwd: empty input");
   TATT_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
@@ -410,11 +437,13 @@ int tatt_bn_bwd(const float* X, const float* dY, const float* mean, const float*
   }
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)ws, C, dgamma, dbeta);
   TATT_LAUNCH_CHECK("bn_bwd_finalize_kernel");
-  if (dX) {
+  if (dX || dx_hi) {
     TATT_REQUIRE(C % 4 == 0, "bn_bwd: C must be a multiple of 4");
     long long total4 = P * C / 4;
     bn_bwd_apply_kernel<<<ew_blocks(total4), 256, 0, st>>>(X, dY, mean, invstd, gamma, beta, dgamma, dbeta, act,
-                                                           training, 1.f / (float)P, total4, C / 4, dX);
+                                                           training, 1.f / (float)P, total4, C / 4, dX,
+                                                           reinterpret_cast<__nv_bfloat16*>(dx_hi),
+                                                           reinterpret_cast<__nv_bfloat16*>(dx_lo));
     TATT_LAUNCH_CHECK("bn_bwd_apply_kernel");
   }
   return 0;

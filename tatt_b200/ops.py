@@ -483,7 +483,7 @@ class _NoSide:
 
 
 def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True, need_dw: bool = True,
-               has_bias: bool = True, keep: Optional[dict] = None, side=None):
+               has_bias: bool = True, keep: Optional[dict] = None, side=None, dy_planes: bool = False):
     """-> (dx [N,H,W,CinP] | None, dW [Cout,Cin,KH,KW] | None, db [Cout] | None).
     `side(*reads)` (optional, the tape's) returns a context manager that runs the enclosed launches on the side
     stream: the weight gradient (and the bias gradient) only feed the optimizer, so they run there, concurrently with
@@ -511,7 +511,14 @@ def conv2d_bwd(x: Tensor, w: Tensor, dy: Tensor, pad: int, need_dx: bool = True,
              and cout_p in (64, 128, 192, 256) and P >= 128)
     dy2 = dy.view(-1, cout_p)
     dy_valid = False
-    if share and need_dw and wd % 64 == 0:
+    if dy_planes:
+        # the producer of dY (a train-mode BatchNorm backward) wrote the planes itself; dY's column sums -- the bias
+        # gradient -- are exactly zero behind a train-mode BatchNorm (sum_p dX_bn = 0)
+        assert share and wd % 64 == 0
+        if has_bias:
+            db = zeros(co, like=x)
+        dy_valid = True
+    elif share and need_dw and wd % 64 == 0:
         # one split of dY on this stream serves both passes; its column sums are the bias gradient
         off = 4 * _r8(x.numel())
         dbp = empty(cout_p, like=x) if has_bias else None
@@ -607,6 +614,34 @@ def bn_bwd(x2: Tensor, dy2: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor,
     _cabi.call("tatt_bn_bwd", _p(x2), _p(dy2), _p(mean), _p(invstd), _p(gamma), _p(beta), act, 1 if training else 0,
                P, C, _p(dx), _p(dg[0]), _p(dg[1]), _p(ws), _stream())
     return dx, dg[0], dg[1]
+
+
+def bn_bwd_planes(x2: Tensor, dy2: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, act: int,
+                  hi_ptr: int, lo_ptr: int):
+    """train-mode BatchNorm backward whose dX goes straight into the bf16 operand planes at (hi_ptr, lo_ptr) -- the dY
+    slot of the workspace of the convolution in front (see conv_dy_plane_ptrs); -> (dgamma, dbeta)"""
+    P, C = x2.shape
+    dg = empty(2, C, like=x2)
+    ws = torch.empty(2 * C, dtype=torch.float64, device=x2.device)
+    _cabi.call("tatt_bn_bwd_planes", _p(x2), _p(dy2), _p(mean), _p(invstd), _p(gamma), _p(beta), act, 1, P, C, hi_ptr,
+               lo_ptr, _p(dg[0]), _p(dg[1]), _p(ws), _stream())
+    return dg[0], dg[1]
+
+
+def conv_dy_plane_ptrs(x: Tensor, cout_p: int, ws: Tensor) -> Tuple[int, int]:
+    """addresses of the dY hi / lo planes inside a convolution workspace (layout of _conv_ws / conv2d_bwd)"""
+    P = x.numel() // x.shape[-1]
+    off = 4 * _r8(x.numel())
+    return ws.data_ptr() + off, ws.data_ptr() + off + 2 * _r8(P * cout_p)
+
+
+def conv_bwd_shares_dy(x: Tensor, w: Tensor, pad: int, ws: Optional[Tensor]) -> bool:
+    """conv2d_bwd will run both backward passes of this layer on the dY planes behind the X planes of `ws`"""
+    n, h, wd, cin_p = x.shape
+    co, ci, kh, kw = w.shape
+    cout_p = _pad4(co)
+    return (ws is not None and _conv_share_dy and not (_precision_flag & F_FP32) and kh == 3 and kw == 3 and pad == 1
+            and cin_p == 64 and cout_p in (64, 128, 192, 256) and n * h * wd >= 128 and wd % 64 == 0)
 
 
 def layernorm_fwd(x2: Tensor, r2: Optional[Tensor], gamma: Tensor, beta: Tensor, save: bool):

@@ -21,6 +21,7 @@ class Tape:
         self._ops: List = []
         self._g: Dict[int, Tensor] = {}
         self._keep: List[Tensor] = []
+        self._conv_keep: Dict[int, tuple] = {}   # conv outputs whose BatchNorm may write the conv's dY planes directly
         self._stats: Dict[int, tuple] = {}   # conv outputs whose BatchNorm sums were produced by the conv kernel itself
         self._side_keep: List = []    # tensors read by side-stream kernels: kept alive until the join (see backward())
         self._pflag = None            # inside precision_scope(flag): forward ops AND their backward closures run in that mode
@@ -185,6 +186,9 @@ class Tape:
         y = ops.conv2d_fwd(x4, w, b, pad, keep=keep, relu=relu, stats=st)
         if st:
             self._stats[id(y)] = (y, st["acc"])
+        if bn_next and self.record and need_dx and ops.conv_bwd_shares_dy(x4, w, pad, keep.get("ws")):
+            # the BatchNorm that consumes y may write its dX straight into this layer's dY planes (batchnorm())
+            self._conv_keep[id(y)] = (y, keep, x4, ops._pad4(w.shape[0]))
 
         def bwd():
             dy = self.grad(y)
@@ -193,7 +197,7 @@ class Tape:
             if relu:
                 dy = ops.relu_bwd(y, dy)
             dx, dw, db = ops.conv2d_bwd(x4, w, dy, pad, need_dx=need_dx, has_bias=b is not None, keep=keep,
-                                        side=self._side)
+                                        side=self._side, dy_planes=bool(keep.get("dy_planes")))
             self.add_grad(w, dw)
             if b is not None:
                 self.add_grad(b, db)
@@ -226,10 +230,22 @@ class Tape:
             mean, invstd = ops.bn_eval_stats(bn.running_mean, bn.running_var, bn.eps)
         gamma, beta = bn.weight, bn.bias
         y = ops.bn_apply(x2, mean, invstd, gamma, beta, act).view(x.shape)
+        ck = self._conv_keep.pop(id(x), None)
+        if ck is not None and not (ck[0] is x and use_batch and training):
+            ck = None
 
         def bwd():
             dy = self.grad(y)
             if dy is None:
+                return
+            if ck is not None and self.grad(x) is None and ck[1].get("ws") is not None:
+                # x is the output of a 3x3 convolution: dX is only ever read as that layer's dY operand planes
+                hi, lo = ops.conv_dy_plane_ptrs(ck[2], ck[3], ck[1]["ws"])
+                dg, db = ops.bn_bwd_planes(x2, dy.view(-1, C), mean, invstd, gamma, beta, act, hi, lo)
+                ck[1]["dy_planes"] = True
+                self.add_grad(gamma, dg)
+                self.add_grad(beta, db)
+                self.add_grad(x, torch.empty(1, dtype=x.dtype, device=x.device).expand(x.shape))   # marker, never read
                 return
             dx, dg, db = ops.bn_bwd(x2, dy.view(-1, C), mean, invstd, gamma, beta, act, use_batch)
             self.add_grad(gamma, dg)
