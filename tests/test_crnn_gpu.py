@@ -2,9 +2,10 @@
 generated from the LIVE reference `model/crnn/crnn.py:CRNN(32, 1, 37, 256)` (tests/golden/make_golden_crnn.py) and
 against the CPU oracle (oracle/crnn_oracle.py, itself bit-exact vs the live class).  Tolerances: pre-processing 1e-5;
 logits 1e-3 of max-abs (measured 3e-5); BatchNorm running statistics 1e-4.
-Gradients vs the fp64 oracle: everything downstream of the last ReLU / max-pool (conv6, batchnorm6, both BiLSTMs and
-their embeddings) 1e-3 rel-L2 per parameter (measured 4e-5..8e-5) -- that is the smooth part, where the bound tests the
-kernels.  The 6 convolution blocks below it are piecewise linear: a forward pass that is accurate to 3e-5 decides a
+Gradients vs the fp64 oracle: everything downstream of the last ReLU (both BiLSTMs and their embeddings) 1e-3 rel-L2 per
+parameter (measured 4e-5..8e-5) -- that is the smooth part, where the bound tests the kernels.  The 7 convolution blocks
+below it (conv6 / batchnorm6 sit in front of the last ReLU: 7e-5 in most runs, 3e-3 when one of its 40 k signs flips) are
+piecewise linear: a forward pass that is accurate to 3e-5 decides a
 handful of the ~10^5 ReLU signs / pooling arg-maxes per layer differently, and every flipped decision moves ALL upstream
 gradients by ~1/sqrt(#active elements) (measured with tools/diag_crnn.py: 3e-3 at conv5 growing to 2e-2 at conv0 in the
 tensor-core mode, 8e-4..1e-3 on the fp32 FFMA kernels whose forward error is 3e-6, 2e-6 for torch CPU fp32).  So the
@@ -83,7 +84,7 @@ def test_crnn_eval_and_train_vs_reference_fixture_and_oracle():
             if n in ("cnn.conv2.bias", "cnn.conv4.bias", "cnn.conv6.bias"):
                 assert g.abs().max().item() <= 1e-4 * G, n          # exactly-zero gradient (train-mode BatchNorm follows)
                 continue
-            smooth = n.startswith("rnn.") or n.startswith("cnn.conv6") or n.startswith("cnn.batchnorm6")
+            smooth = n.startswith("rnn.")
             rel = (g.double().cpu() - og).norm().item() / max(og.norm().item(), 1e-6 * G * og.numel() ** 0.5)
             if rel > (1e-3 if smooth else tol_cnn):
                 bad.append("%s %.2e" % (n, rel))
@@ -96,7 +97,7 @@ def test_crnn_eval_and_train_vs_reference_fixture_and_oracle():
         if n in ("cnn.conv2.bias", "cnn.conv4.bias", "cnn.conv6.bias"):
             continue
         got = p.grad.detach().cpu().reshape(-1)[ref["idx"]]
-        smooth = n.startswith("rnn.") or n.startswith("cnn.conv6") or n.startswith("cnn.batchnorm6")
+        smooth = n.startswith("rnn.")
         rel = (got - ref["val"]).norm().item() / max(ref["val"].norm().item(), 1e-6 * G * got.numel() ** 0.5)
         assert rel <= (1e-3 if smooth else 6e-2), "%s: sampled gradient vs live-reference fixture rel-L2 %.2e" % (n, rel)
     from tatt_b200 import ops
