@@ -125,6 +125,10 @@ int tatt_bn_eval_stats(const float* running_mean, const float* running_var, floa
                        float* invstd, void* stream);
 int tatt_bn_apply_fwd(const float* X, float* Y, const float* mean, const float* invstd, const float* gamma,
                       const float* beta, int act, long long P, int C, void* stream);
+/* the same normalisation + activation, written ONLY as bf16 hi / lo planes [P][C]: for a BatchNorm whose single consumer
+ * is a convolution (tsrn.py:897: bn1 + mish -> conv2), the planes are that convolution's X operand (flag 2048) */
+int tatt_bn_apply_planes(const float* X, void* y_hi, void* y_lo, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, int act, long long P, int C, void* stream);
 int tatt_bn_bwd(const float* X, const float* dY, const float* mean, const float* invstd, const float* gamma,
                 const float* beta, int act, int training, long long P, int C, float* dX, float* dgamma,
                 float* dbeta, void* ws, void* stream);
@@ -204,6 +208,10 @@ int tatt_prelu_fwd(const float* x, const float* w, float* y, long long n, void* 
 int tatt_prelu_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, long long n,
                    void* stream);
 int tatt_pixshuf2_mish_fwd(const float* in, float* out, long long nimg, int H, int W, int C, void* stream);
+/* PixelShuffle(2) + mish written as bf16 hi / lo planes [N*2H*2W][C]: the X operand of the convolution that follows
+ * (tsrn.py:623 after 1049-1053) */
+int tatt_pixshuf2_mish_planes(const float* in, void* out_hi, void* out_lo, long long nimg, int H, int W, int C,
+                              void* stream);
 int tatt_pixshuf2_mish_bwd(const float* in, const float* dout, float* din, long long nimg, int H, int W, int C,
                            void* stream);
 int tatt_nchw_to_nhwc(const float* in, float* out, long long N, int C, int H, int W, int Cp, void* stream);

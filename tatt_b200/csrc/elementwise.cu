@@ -2,6 +2,7 @@
 // Reference ops replaced: nn.PReLU (tsrn.py:598, 173), mish (tsrn.py:1061-1064), nn.PixelShuffle
 // (tsrn.py:1046), torch.tanh (tsrn.py:675), nn.Dropout (transformer_v2.py:29,455,461-462,788,795-797),
 // the NCHW<->NHWC permutes around GruBlock (tsrn.py:1076-1083) and the residual adds.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -92,6 +93,28 @@ __global__ void pixshuf_mish_fwd_kernel(const float* __restrict__ in, float* __r
     o[C] = mish_f(v.y);
     o[orow] = mish_f(v.z);
     o[orow + C] = mish_f(v.w);
+  }
+}
+// the same map, written as bf16 hi / lo planes [N*2H*2W][C] (X operand of the convolution that follows the up-sampler)
+__global__ void pixshuf_mish_planes_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                           __nv_bfloat16* __restrict__ lo, long long npix_in, int H, int W, int C) {
+  const long long n = npix_in * C;
+  const long long orow = 2LL * W * C;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    const long long p = i / C;
+    const int w = (int)(p % W);
+    const long long q = p / W;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    const long long o = (2 * q) * orow + (2LL * w) * C + c;
+    const float y[4] = {mish_f(v.x), mish_f(v.y), mish_f(v.z), mish_f(v.w)};
+    const long long off[4] = {0, C, orow, orow + C};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(y[k]);
+      hi[o + off[k]] = h;
+      lo[o + off[k]] = __float2bfloat16_rn(y[k] - __bfloat162float(h));
+    }
   }
 }
 __global__ void pixshuf_mish_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout,
@@ -403,6 +426,16 @@ int tatt_pixshuf2_mish_fwd(const float* in, float* out, long long nimg, int H, i
   if (npix_in <= 0) return 0;
   pixshuf_mish_fwd_kernel<<<ew_blocks(npix_in * C), 256, 0, (cudaStream_t)stream>>>(in, out, npix_in, H, W, C);
   TATT_LAUNCH_CHECK("pixshuf_mish_fwd_kernel");
+  return 0;
+}
+int tatt_pixshuf2_mish_planes(const float* in, void* out_hi, void* out_lo, long long nimg, int H, int W, int C,
+                              void* stream) {
+  long long npix_in = nimg * (long long)H * W;
+  if (npix_in <= 0) return 0;
+  TATT_REQUIRE(out_hi && out_lo, "pixshuf2_mish_planes: null planes");
+  pixshuf_mish_planes_kernel<<<ew_blocks(npix_in * C), 256, 0, (cudaStream_t)stream>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), npix_in, H, W, C);
+  TATT_LAUNCH_CHECK("pixshuf_mish_planes_kernel");
   return 0;
 }
 int tatt_pixshuf2_mish_bwd(const float* in, const float* dout, float* din, long long nimg, int H, int W, int C,

@@ -138,7 +138,8 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* 
 // Y = act(X * scale + shift)   (C % 4 == 0)
 __global__ void bn_apply_kernel(const float* __restrict__ X, float* __restrict__ Y, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int act, long long total4, int C4) {
+                                const float* __restrict__ beta, int act, long long total4, int C4,
+                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C4) * 4;
@@ -152,7 +153,15 @@ __global__ void bn_apply_kernel(const float* __restrict__ X, float* __restrict__
     y.y = act_fwd((x.y - m.y) * is.y * g.y + b.y, act);
     y.z = act_fwd((x.z - m.z) * is.z * g.z + b.z, act);
     y.w = act_fwd((x.w - m.w) * is.w * g.w + b.w, act);
-    reinterpret_cast<float4*>(Y)[i] = y;
+    if (hi) {           // only consumer is a convolution: bf16 hi / lo operand planes instead of the fp32 tensor
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(y.x, y.y), h1 = __floats2bfloat162_rn(y.z, y.w);
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(y.x - f0.x, y.y - f0.y), l1 = __floats2bfloat162_rn(y.z - f1.x, y.w - f1.y);
+      reinterpret_cast<uint2*>(hi)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      reinterpret_cast<uint2*>(lo)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    } else {
+      reinterpret_cast<float4*>(Y)[i] = y;
+    }
   }
 }
 
@@ -393,7 +402,20 @@ int tatt_bn_apply_fwd(const float* X, float* Y, const float* mean, const float* 
   long long total4 = P * C / 4;
   if (total4 == 0) return 0;
   bn_apply_kernel<<<ew_blocks(total4), 256, 0, (cudaStream_t)stream>>>(X, Y, mean, invstd, gamma, beta, act,
-                                                                       total4, C / 4);
+                                                                       total4, C / 4, nullptr, nullptr);
+  TATT_LAUNCH_CHECK("bn_apply_kernel");
+  return 0;
+}
+// the same, written only as bf16 hi / lo planes [P][C] (the X operand of the convolution that consumes it)
+int tatt_bn_apply_planes(const float* X, void* y_hi, void* y_lo, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, int act, long long P, int C, void* stream) {
+  TATT_REQUIRE(C % 4 == 0 && y_hi && y_lo && ((((uintptr_t)y_hi) | ((uintptr_t)y_lo)) & 7) == 0,
+               "bn_apply_planes: C %% 4 == 0 and 8-byte aligned planes required");
+  long long total4 = P * C / 4;
+  if (total4 == 0) return 0;
+  bn_apply_kernel<<<ew_blocks(total4), 256, 0, (cudaStream_t)stream>>>(X, nullptr, mean, invstd, gamma, beta, act, total4,
+                                                                       C / 4, reinterpret_cast<__nv_bfloat16*>(y_hi),
+                                                                       reinterpret_cast<__nv_bfloat16*>(y_lo));
   TATT_LAUNCH_CHECK("bn_apply_kernel");
   return 0;
 }

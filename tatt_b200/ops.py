@@ -421,14 +421,47 @@ def _conv_ws(x: Tensor, nx: int, ndy: int, extra: int):
     return torch.empty(nbytes, dtype=torch.uint8, device=x.device)
 
 
+def conv_fwd_ws_elems(cin_p: int, cout_p: int, kh: int, kw: int, P: int) -> Tuple[int, int]:
+    """(dY-plane elements, extra elements) of a convolution layer's workspace (see _conv_ws)"""
+    if cout_p == 4 and kw > 1 and cin_p >= 16:
+        return P * _r8(kw * 4), kh * cin_p * _r8(kw * 4) + 148 * kh * cin_p * _r8(kw * 4)
+    return P * _r8(cout_p), (max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p))
+                             + 148 * kh * kw * cin_p * cout_p + 16)
+
+
+def conv_x_planes_ok(shape, w: Tensor) -> bool:
+    """a producer may hand this convolution its input as bf16 planes only: every engine that can serve the layer reads
+    pre-split planes (flag 2048) and never the fp32 tensor"""
+    n, h, wd, cin_p = shape
+    return (_producer_planes and not (_precision_flag & F_FP32) and cin_p == 64 and n * h * wd >= 128
+            and w.shape[1] <= 64 and w.shape[0] >= 3)
+
+
+# off when a debugging switch routes convolutions to an engine without pre-split operand planes (or TATT_XPLANES=0)
+_producer_planes = all(os.environ.get(k, "1") != "0" for k in ("TATT_XPLANES", "TATT_TC", "TATT_TC2"))
+
+
+def conv_x_planes_alloc(shape, w: Tensor, like: Tensor):
+    """workspace of the layer (same layout as conv2d_fwd allocates) + addresses of its X hi / lo planes"""
+    n, h, wd, cin_p = shape
+    co, ci, kh, kw = w.shape
+    P = n * h * wd
+    ndy, extra = conv_fwd_ws_elems(cin_p, _pad4(co), kh, kw, P)
+    ws = _conv_ws(like, P * cin_p, ndy, extra)
+    return ws, ws.data_ptr(), ws.data_ptr() + 2 * _r8(P * cin_p)
+
+
 def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Optional[dict] = None,
-               relu: bool = False, stats: Optional[dict] = None) -> Tensor:
+               relu: bool = False, stats: Optional[dict] = None, ws_pre: Optional[Tensor] = None) -> Tensor:
     """x [N,H,W,CinP] (CinP >= w.shape[1], multiple of 4) -> y [N,H,W,CoutP] (same H x W: out-of-image taps read 0).
     `keep` (a dict owned by the caller's tape entry) receives the workspace whose X planes the backward pass reuses;
     `relu` fuses max(., 0) into the epilogue (generic engine only); `stats` (a dict) receives under "acc" the
     per-channel {sum, sum of squares} of y (2*Cout doubles) when the layer is served by the kernel that produces them
-    in its epilogue (tatt_conv3x3_stats) -- the BatchNorm that follows then skips its own statistics pass."""
+    in its epilogue (tatt_conv3x3_stats) -- the BatchNorm that follows then skips its own statistics pass.
+    `ws_pre`: the layer's workspace with the X planes ALREADY written by the producer of x (conv_x_planes_alloc); x itself
+    is then only a shape carrier and is never read."""
     n, h, wd, cin_p = x.shape
+    xv = F_A_VALID if ws_pre is not None else 0
     co, ci, kh, kw = w.shape
     cout_p = _pad4(co)
     if b is not None and cout_p != co:
@@ -442,9 +475,10 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Option
         wte = empty(kh * cin_p, kw * 4, like=x)
         _cabi.call("tatt_conv_kxexp_pack", _p(w.contiguous()), _p(wte), co, ci, kh, kw, cin_p, 4, _stream())
         t = empty(P, kw * 4, like=x)
-        ws = _conv_ws(x, x.numel(), P * _r8(kw * 4), kh * cin_p * _r8(kw * 4) + 148 * kh * cin_p * _r8(kw * 4))
+        ws = ws_pre if ws_pre is not None else _conv_ws(
+            x, x.numel(), P * _r8(kw * 4), kh * cin_p * _r8(kw * 4) + 148 * kh * cin_p * _r8(kw * 4))
         _cabi.call("tatt_conv2d_igemm", _p(x), _p(wte), None, _p(t), n, h, wd, cin_p, kw * 4, kh, 1, pad, 0,
-                   _precision_flag, _p(ws), 0 if ws is None else ws.numel(), _stream())
+                   _precision_flag | xv, _p(ws), 0 if ws is None else ws.numel(), _stream())
         _cabi.call("tatt_conv_kxexp_reduce", _p(t), _p(b), _p(y), P, wd, kw, 4, pad, _stream())
         if keep is not None:
             keep["ws"] = ws
@@ -452,19 +486,21 @@ def conv2d_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], pad: int, keep: Option
     wt = conv_pack(w, cin_p, cout_p, False)
     if (stats is not None and kh == 3 and kw == 3 and pad == 1 and not relu and not (_precision_flag & F_FP32)
             and _cabi.lib().tatt_conv3x3_stats_supported(h, wd, cin_p, cout_p)):
-        ws = _conv_ws(x, x.numel(), P * _r8(cout_p),
-                      max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
+        ws = ws_pre if ws_pre is not None else _conv_ws(
+            x, x.numel(), P * _r8(cout_p),
+            max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
         acc = torch.empty(CONV_STATS_ROWS, 2 * cout_p, dtype=torch.float32, device=x.device)   # one row per CTA
-        _cabi.call("tatt_conv3x3_stats", _p(x), _p(wt), _p(b), _p(y), n, h, wd, _precision_flag, _p(ws), ws.numel(),
+        _cabi.call("tatt_conv3x3_stats", _p(x), _p(wt), _p(b), _p(y), n, h, wd, _precision_flag | xv, _p(ws), ws.numel(),
                    _p(acc), _stream())
         stats["acc"] = acc
         if keep is not None:
             keep["ws"] = ws
         return y
-    ws = _conv_ws(x, x.numel(), P * _r8(cout_p),
-                  max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
+    ws = ws_pre if ws_pre is not None else _conv_ws(
+        x, x.numel(), P * _r8(cout_p),
+        max(kh * kw * cin_p * _r8(cout_p), kh * kw * cout_p * _r8(cin_p)) + 148 * kh * kw * cin_p * cout_p + 16)
     _cabi.call("tatt_conv2d_igemm", _p(x), _p(wt), _p(b), _p(y), n, h, wd, cin_p, cout_p, kh, kw, pad, pad,
-               _precision_flag | (F_RELU if relu else 0), _p(ws), 0 if ws is None else ws.numel(), _stream())
+               _precision_flag | (F_RELU if relu else 0) | xv, _p(ws), 0 if ws is None else ws.numel(), _stream())
     if keep is not None:
         keep["ws"] = ws
     return y
@@ -603,6 +639,13 @@ def bn_apply(x2: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tens
     y = torch.empty_like(x2)
     _cabi.call("tatt_bn_apply_fwd", _p(x2), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), act, P, C, _stream())
     return y
+
+
+def bn_apply_planes(x2: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, act: int, hi_ptr: int,
+                    lo_ptr: int) -> None:
+    P, C = x2.shape
+    _cabi.call("tatt_bn_apply_planes", _p(x2), hi_ptr, lo_ptr, _p(mean), _p(invstd), _p(gamma), _p(beta), act, P, C,
+               _stream())
 
 
 def bn_bwd(x2: Tensor, dy2: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, act: int,
@@ -799,6 +842,11 @@ def pixshuf2_mish_fwd(x: Tensor) -> Tensor:
     out = empty(n, 2 * h, 2 * w, c4 // 4, like=x)
     _cabi.call("tatt_pixshuf2_mish_fwd", _p(x), _p(out), n, h, w, c4 // 4, _stream())
     return out
+
+
+def pixshuf2_mish_planes(x: Tensor, hi_ptr: int, lo_ptr: int) -> None:
+    n, h, w, c4 = x.shape
+    _cabi.call("tatt_pixshuf2_mish_planes", _p(x), hi_ptr, lo_ptr, n, h, w, c4 // 4, _stream())
 
 
 def pixshuf2_mish_bwd(x: Tensor, dout: Tensor) -> Tensor:

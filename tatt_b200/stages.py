@@ -148,7 +148,7 @@ def srb_stage(blk: torch.nn.Module, x: Tensor, tp_map: Optional[Tensor], trainin
             raise NotImplementedError("tatt_b200 kernels are specialised for hidden_units=32 (64 channels)")
         tp4 = as_nhwc(t[1]) if tp_map is not None else None
         r = tape.conv(x4, blk.conv1.weight, blk.conv1.bias, 1, bn_next=training)
-        r = tape.batchnorm(r, blk.bn1, ops.ACT_MISH, training)
+        r = tape.batchnorm(r, blk.bn1, ops.ACT_MISH, training, planes_for=blk.conv2.weight)   # only consumer: conv2
         r = tape.conv(r, blk.conv2.weight, blk.conv2.bias, 1, bn_next=training)
         r = tape.batchnorm(r, blk.bn2, ops.ACT_NONE, training)
         parts = [tape.view(r, -1, C)] + ([tape.view(tp4, -1, tp4.shape[-1])] if tp4 is not None else [])
@@ -405,8 +405,9 @@ def tail_stage(seq: torch.nn.Sequential, skip_a: Tensor, skip_b: Tensor, out_pla
     def build(tape: Tape, t):
         a4, b4 = as_nhwc(t[0]), as_nhwc(t[1])
         s = tape.add(a4, b4)
-        for u in ups:
-            s = tape.pixshuf_mish(tape.conv(s, u.conv.weight, u.conv.bias, u.conv.padding[0]))
+        for i, u in enumerate(ups):
+            nxt = ups[i + 1].conv if i + 1 < len(ups) else final            # the only consumer of the up-sampled map
+            s = tape.pixshuf_mish(tape.conv(s, u.conv.weight, u.conv.bias, u.conv.padding[0]), planes_for=nxt.weight)
         pre = tape.conv(s, final.weight, final.bias, final.padding[0])
         out = tape.to_nchw(pre, out_planes, tanh=True)
         pre_view = expose_nchw(pre)[:, :out_planes]

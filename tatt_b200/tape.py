@@ -21,6 +21,7 @@ class Tape:
         self._ops: List = []
         self._g: Dict[int, Tensor] = {}
         self._keep: List[Tensor] = []
+        self._xplanes: Dict[int, tuple] = {}     # shape-carrier tensors whose values exist only as a conv's X planes
         self._conv_keep: Dict[int, tuple] = {}   # conv outputs whose BatchNorm may write the conv's dY planes directly
         self._stats: Dict[int, tuple] = {}   # conv outputs whose BatchNorm sums were produced by the conv kernel itself
         self._side_keep: List = []    # tensors read by side-stream kernels: kept alive until the join (see backward())
@@ -183,7 +184,10 @@ class Tape:
         statistics in the epilogue when it can (picked up by batchnorm() through self._stats)."""
         keep = {} if self.record else None       # workspace whose X planes the backward pass reuses
         st = {} if bn_next else None
-        y = ops.conv2d_fwd(x4, w, b, pad, keep=keep, relu=relu, stats=st)
+        pre = self._xplanes.pop(id(x4), None)    # the producer wrote the X planes of THIS layer (x4 carries the shape only)
+        if pre is not None:
+            assert pre[0] is x4 and pre[2] is w, "operand planes were prepared for another convolution"
+        y = ops.conv2d_fwd(x4, w, b, pad, keep=keep, relu=relu, stats=st, ws_pre=None if pre is None else pre[1])
         if st:
             self._stats[id(y)] = (y, st["acc"])
         if bn_next and self.record and need_dx and ops.conv_bwd_shares_dy(x4, w, pad, keep.get("ws")):
@@ -207,8 +211,18 @@ class Tape:
         return y
 
     # ------------------------------------------------------------------ normalisation
-    def batchnorm(self, x: Tensor, bn: torch.nn.Module, act: int, training: bool) -> Tensor:
-        """BatchNorm over all leading dims of a channels-last tensor, fused activation."""
+    def _planes_carrier(self, shape, w: Tensor, like: Tensor):
+        """-> (shape-carrier tensor y, hi address, lo address): y has no values, they go to the X planes of the conv `w`"""
+        ws, hi, lo = ops.conv_x_planes_alloc(shape, w, like)
+        y = torch.empty(1, dtype=like.dtype, device=like.device).expand(shape)
+        self._xplanes[id(y)] = (y, ws, w)
+        return y, hi, lo
+
+    def batchnorm(self, x: Tensor, bn: torch.nn.Module, act: int, training: bool,
+                  planes_for: Optional[Tensor] = None) -> Tensor:
+        """BatchNorm over all leading dims of a channels-last tensor, fused activation.  planes_for = weight of the
+        convolution that is the ONLY consumer of the result: the result is then written as that layer's bf16 operand
+        planes and the returned tensor only carries the shape (pass it to conv() and nothing else)."""
         C = x.shape[-1]
         x2 = x.view(-1, C)
         use_batch = training or bn.running_mean is None
@@ -229,7 +243,11 @@ class Tape:
         else:
             mean, invstd = ops.bn_eval_stats(bn.running_mean, bn.running_var, bn.eps)
         gamma, beta = bn.weight, bn.bias
-        y = ops.bn_apply(x2, mean, invstd, gamma, beta, act).view(x.shape)
+        if planes_for is not None and x.dim() == 4 and ops.conv_x_planes_ok(x.shape, planes_for):
+            y, hi, lo = self._planes_carrier(x.shape, planes_for, x)
+            ops.bn_apply_planes(x2, mean, invstd, gamma, beta, act, hi, lo)
+        else:
+            y = ops.bn_apply(x2, mean, invstd, gamma, beta, act).view(x.shape)
         ck = self._conv_keep.pop(id(x), None)
         if ck is not None and not (ck[0] is x and use_batch and training):
             ck = None
@@ -340,8 +358,15 @@ class Tape:
         self._push(bwd)
         return y
 
-    def pixshuf_mish(self, x4: Tensor) -> Tensor:
-        y = ops.pixshuf2_mish_fwd(x4)
+    def pixshuf_mish(self, x4: Tensor, planes_for: Optional[Tensor] = None) -> Tensor:
+        """planes_for: as in batchnorm() -- the up-sampled map is consumed by one convolution only"""
+        n, h, w_, c4 = x4.shape
+        oshape = (n, 2 * h, 2 * w_, c4 // 4)
+        if planes_for is not None and ops.conv_x_planes_ok(oshape, planes_for):
+            y, hi, lo = self._planes_carrier(oshape, planes_for, x4)
+            ops.pixshuf2_mish_planes(x4, hi, lo)
+        else:
+            y = ops.pixshuf2_mish_fwd(x4)
 
         def bwd():
             dy = self.grad(y)
