@@ -5,6 +5,7 @@
 // Q/K/V ([N][L][64], token-major); the kernel does scale, QK^T, softmax, (dropout), PV and the
 // head-averaged weights nn.MultiheadAttention returns (need_weights=True).
 // One CTA = 32 queries x 4 heads (warp == head, lane == query); K/V of the sample live in SMEM.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -310,6 +311,11 @@ mha_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const f
 
 }  // namespace
 
+// warp-level tensor-core version of the backward (attn_mma.cu)
+int tatt_mha64_bwd_mma_launch(const float* Q, const float* K, const float* V, const float* dO, float* dQ, float* dK,
+                              float* dV, int N, int Lq, int Lk, float pdrop, const unsigned long long* rng,
+                              unsigned long long site, cudaStream_t st);
+
 extern "C" {
 
 // Q [N][Lq][64], K/V [N][Lk][64] (projected, unscaled) -> O [N][Lq][64]; AW [N][Lq][Lk] head-averaged
@@ -337,6 +343,11 @@ int tatt_mha64_bwd(const float* Q, const float* K, const float* V, const float* 
   TATT_CUDA(cudaMemsetAsync(dK, 0, sizeof(float) * (size_t)N * Lk * DM, st));
   TATT_CUDA(cudaMemsetAsync(dV, 0, sizeof(float) * (size_t)N * Lk * DM, st));
   if (Lq <= 0) return 0;
+  static const bool use_mma = []() {               // TATT_MHA_MMA=0: the CUDA-core kernel below
+    const char* e = getenv("TATT_MHA_MMA");
+    return !(e && e[0] == '0');
+  }();
+  if (use_mma) return tatt_mha64_bwd_mma_launch(Q, K, V, dO, dQ, dK, dV, N, Lq, Lk, pdrop, rng, site, st);
   TATT_CUDA(cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(BwdSmem)));
   int ntiles = (Lq + 31) / 32;
