@@ -306,6 +306,8 @@ def tp_stage(ig: torch.nn.Module, feat: Tensor, text_emb: Tensor, qpos: Tensor, 
         if Nt != N:
             raise RuntimeError("text prior batch (%d) != image batch (%d); the reference only broadcasts "
                                "the default zeros prior for N == 1" % (Nt, N))
+        if not t[2].is_contiguous():
+            ops.join_side()            # a copy kernel would read qpos before the join below
         qp_raw = t[2].contiguous()
         qp = tape.view(qp_raw, N * H * W, C)
         tgt = tape.view(f4, N * H * W, C)
@@ -345,6 +347,7 @@ def tp_stage(ig: torch.nn.Module, feat: Tensor, text_emb: Tensor, qpos: Tensor, 
         inter = []
         aw = None
         fused = ops.declayer_ok(N, H * W, L) and C == 64 and all(dd.linear1.weight.shape == (64, 64) for dd in decs)
+        ops.join_side()                # qpos may still be in flight on the side stream (tsrn.TSRN_TL_TRANS.forward)
         for i, d in enumerate(decs):
             last = i == len(decs) - 1
             if fused:          # one tcgen05 kernel per decoder layer (csrc/tc6_declayer.cu)

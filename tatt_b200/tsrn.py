@@ -394,7 +394,8 @@ class TSRN_TL_TRANS(_TSRNBase):
             with stages.ops.side_stream():
                 qpos = self.infoGen.query_pos(text_emb.shape[0], x.shape[2], x.shape[3])
         block = {"1": self._stem(x)}
-        stages.ops.join_side()
+        # (the side stream is joined inside the TP stage, right before the first decoder layer reads qpos: the text
+        # branch -- fc_in, PReLU, the encoder layer, K / V projections -- still overlaps the recurrence)
         tp_map, pr_weights = self.infoGen(block["1"], text_emb, qpos)
         k = self.srb_nums + 2
         for i in range(2, k + 1):

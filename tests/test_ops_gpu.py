@@ -65,7 +65,8 @@ def test_gemm_batched_strided():
                                              (2, 16, 64, 64, 256, 3), (2, 6, 10, 4, 32, 3), (2, 2, 8, 128, 256, 3),
                                              (1, 1, 2, 256, 256, 3), (2, 8, 8, 3, 64, 9), (2, 8, 8, 64, 3, 9),
                                              (2, 4, 128, 64, 64, 3), (1, 6, 256, 64, 64, 3), (5, 8, 128, 64, 64, 3),
-                                             (40, 16, 128, 64, 64, 3), (3, 2, 128, 64, 64, 3)])   # last five: TMA halo kernels (persistent rolling-halo variant: strips, fresh / rolling tiles, > 148 tiles)
+                                             (40, 16, 128, 64, 64, 3), (3, 2, 128, 64, 64, 3),
+                                             (2, 4, 128, 64, 256, 3), (3, 8, 128, 64, 128, 3)])   # last seven: TMA halo kernels (the last two with 4 / 2 output-channel groups); (persistent rolling-halo variant: strips, fresh / rolling tiles, > 148 tiles)
 def test_conv2d_fwd_bwd(N, H, W, Cin, Cout, k):
     from tatt_b200 import ops
     pad = k // 2
