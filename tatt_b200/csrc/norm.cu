@@ -332,13 +332,22 @@ static int ew_blocks(long long n, int per = 256) {
 __global__ void bn_finalize_parts_kernel(const float* __restrict__ parts, int nparts, long long P, int C, float eps,
                                          float momentum, float* __restrict__ mean, float* __restrict__ invstd,
                                          float* __restrict__ running_mean, float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel: lanes stride over the rows (a single thread walking the ~150 rows took 27 us on the critical
+  // path of every convolution block), fixed-order shuffle reduction in double
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < nparts; ++i) {
+  for (int i = lane; i < nparts; i += 32) {
     s += (double)parts[(long long)i * 2 * C + c];
     q += (double)parts[(long long)i * 2 * C + C + c];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane != 0) return;
   const double m = s / (double)P;
   double var = q / (double)P - m * m;
   if (var < 0.0) var = 0.0;
@@ -350,7 +359,6 @@ __global__ void bn_finalize_parts_kernel(const float* __restrict__ parts, int np
     running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
   }
 }
-
 }  // namespace
 
 extern "C" {
@@ -382,7 +390,7 @@ int tatt_bn_stats(const float* X, long long P, int C, float eps, float momentum,
 int tatt_bn_finalize(const float* parts, int nparts, long long P, int C, float eps, float momentum, float* mean,
                      float* invstd, float* running_mean, float* running_var, void* stream) {
   TATT_REQUIRE(P >= 1 && C >= 1 && nparts >= 1 && parts != nullptr, "bn_finalize: empty input");
-  bn_finalize_parts_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(parts, nparts, P, C, eps, momentum, mean, invstd,
+  bn_finalize_parts_kernel<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(parts, nparts, P, C, eps, momentum, mean, invstd,
                                                                            running_mean, running_var);
   TATT_LAUNCH_CHECK("bn_finalize_parts_kernel");
   return 0;

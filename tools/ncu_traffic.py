@@ -17,6 +17,10 @@ ENTRY = {
     "rows_wgrad1_kernel<3>": "tatt_rows_wgrad NB3",
     "conv3x3_roll_kernel<0, 1>": "tatt_conv2d_igemm 3x3 64->64",
     "mha_bwd_kernel": "tatt_mha64_bwd ",
+    "mha_bwd_mma_kernel": "tatt_mha64_bwd ",
+    "rows_wgrad_kernel<1>": "tatt_rows_wgrad NB1",
+    "gru32_scan_bwd_mma_kernel<0>": "tatt_gru32_scan_bwd T32",
+    "gru32_scan_fwd_mma_kernel<0>": "tatt_gru32_scan_fwd T32",
     "rpe_fwd_persist_kernel": "tatt_rpe_fwd T64 W128 Hd1024",
     "conv3x3_wgrad_tma_kernel": "tatt_conv2d_wgrad 3x3 64->64",
     "tp_declayer_fwd_kernel<1>": "tatt_tp_declayer_fwd ",
