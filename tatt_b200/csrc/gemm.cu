@@ -706,9 +706,9 @@ int tatt_conv2d_igemm(const float* X, const float* Wt, const float* bias, float*
                       void* stream) {
   TATT_REQUIRE(Cin % 4 == 0, "conv2d_igemm: Cin (%d) must be a multiple of 4 (pad channels)", Cin);
   TATT_REQUIRE((long long)nimg * H * W < (1LL << 31), "conv2d_igemm: too many pixels");
-  if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin == 64 && Cout % 64 == 0 && Cout <= 256 && ws &&
+  if (KH == 3 && KW == 3 && padH == 1 && padW == 1 && Cin % 64 == 0 && Cin <= 256 && Cout % 64 == 0 && Cout <= 256 && ws &&
       !(flags & (F_ACCUM | F_RELU | F_FP32))) {
-    int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, Cout, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
+    int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, Cin, Cout, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
                                      ws_bytes, nullptr, (cudaStream_t)stream);
     if (rc >= 0) return rc;
   }
@@ -746,7 +746,7 @@ int tatt_conv3x3_stats(const float* X, const float* Wt, const float* bias, float
   int dev = 0, nsm = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   TATT_REQUIRE(nsm <= TATT_CONV_STATS_ROWS, "conv3x3_stats: device has more SMs (%d) than statistics rows", nsm);
-  int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, 64, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
+  int rc = tatt_tc3_conv3x3_launch(X, Wt, bias, Y, nimg, H, W, 64, 64, (flags & F_BF16) ? 1 : 0, (flags & F_A_VALID) ? 1 : 0, ws,
                                    ws_bytes, reinterpret_cast<float*>(stats), st);
   if (rc < 0) return tatt_set_error("conv3x3_stats: shape [%d,%d,%d] is not served by the TMA kernel", nimg, H, W);
   return rc;

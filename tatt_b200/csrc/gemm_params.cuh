@@ -59,9 +59,9 @@ int tatt_tc2_split(const float* src, long long ld, long long rows, int cols, int
 int tatt_tc2_gemm_launch(GemmP p, int amode, int bmode, bool want_split, void* ws, long long ws_bytes,
                          cudaStream_t st);
 
-// TMA + halo-reuse kernel for the 3x3 / 64->64 convolution (tc3_conv.cu); same return convention
+// TMA + halo-reuse kernel for the 3x3 convolutions with 64 k channels in and out (tc3_conv.cu); same return convention
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
-                            int Cout, int single, int a_valid, void* ws, long long ws_bytes, float* stats,
+                            int Cin, int Cout, int single, int a_valid, void* ws, long long ws_bytes, float* stats,
                             cudaStream_t st);
 int tatt_tc3_conv3x3_wgrad_launch(const float* X, const float* dY, float* dWt, int nimg, int H, int W, int Cout,
                                   int single, int a_valid, int b_valid, void* ws, long long ws_bytes, cudaStream_t st);

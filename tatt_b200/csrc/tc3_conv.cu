@@ -292,7 +292,12 @@ __global__ void __launch_bounds__(192, 1)
 conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                     float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles, int dbg, int ldy,
-                    int ngroups, float* __restrict__ stats) {
+                    int ngroups, float* __restrict__ stats, int ncin) {
+  // C_in = 64 * ncin (ncin > 1 only with one output group): every output tile accumulates ncin x 9 taps in its TMEM
+  // accumulator, input group gi = channels [64 gi, 64 gi + 64) of the [P][C_in] planes = k columns tap * C_in + 64 gi of
+  // the weight planes.  The halo rows of a group cannot roll into the next tile (the four row slots are reloaded per
+  // group), so every (tile, group) is a "fresh" tile; the loads still hide behind the MMAs: rows 0, 1 of the next group
+  // are requested after tap 5, rows 2, 3 after tap 8 and are first needed at the next group's tap 3.
   // C_out = 64 * ngroups: work item w = g * ntiles + t is the 64-channel output group g of pixel tile t (the same halo
   // tile is re-read per group, mostly from L2; every group is the 64 -> 64 problem with its own weight slice)
   constexpr uint32_t acc_stride = cat ? 256u : 128u, row_stride = cat ? 128u : 64u;
@@ -351,33 +356,38 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         const int g = w / ntiles, t = w - g * ntiles;
         const int yb = t % nyb, xb = (t / nyb) % nxt, n = t / (nyb * nxt);
         const int y0 = 2 * yb, x0 = xb * TW;
-        const bool fresh = (w == t0) || (yb == 0);
+        const bool fresh = (w == t0) || (yb == 0) || (ncin > 1);
         const int p0 = (y0 >> 1) & 1;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (k == 0 && !fresh) continue;          // rows y0-1, y0 are already there (previous tile's rows 2, 3)
+        for (int gi = 0; gi < ncin; ++gi) {
+        auto load_pair = [&](int k) {
           const int pr = (k == 0) ? p0 : (p0 ^ 1);
           const int nl = pr ? nload1 : nload0;
           if (nl > 0) mbar_wait(smem_u32(&pair_empty[pr]), (uint32_t)((nl - 1) & 1));
           const uint32_t bar = smem_u32(&pair_full[pr]);
           mbar_expect_tx(bar, pair_bytes);
           const int yy = (k == 0) ? (y0 - 1) : (y0 + 1);
-          tma_load_4d(a_hi + (uint32_t)(pr * PAIR_BYTES), &tmAh, bar, 0, x0 - 1, yy, n);
-          if (!single) tma_load_4d(a_lo + (uint32_t)(pr * PAIR_BYTES), &tmAl, bar, 0, x0 - 1, yy, n);
+          tma_load_4d(a_hi + (uint32_t)(pr * PAIR_BYTES), &tmAh, bar, gi * 64, x0 - 1, yy, n);
+          if (!single) tma_load_4d(a_lo + (uint32_t)(pr * PAIR_BYTES), &tmAl, bar, gi * 64, x0 - 1, yy, n);
           if (pr) ++nload1; else ++nload0;
-        }
+        };
+        if (fresh) load_pair(0);                   // else rows y0-1, y0 are already there (previous tile's rows 2, 3)
+        // rows y0+1, y0+2 are first read at tap 3.  With input groups their slots are released only when the previous
+        // group is done, so the wait sits behind the first three weight taps (else it would hold those back too)
+        if (ncin == 1) load_pair(1);
         for (int tap = 0; tap < 9; ++tap) {
           if ((dbg & 2) && (w > t0 || tap >= RL_NSTAGE)) break;
+          if (ncin > 1 && tap == 3) load_pair(1);
           if (wrapped) mbar_wait(smem_u32(&w_empty[ws]), wpar);
           const uint32_t dst = b_ring + (uint32_t)(ws * B_TAP_BYTES);
           mbar_expect_tx(smem_u32(&w_full[ws]), (uint32_t)(single ? B_TAP_BYTES / 2 : B_TAP_BYTES));
-          tma_load_2d(dst, &tmBh, smem_u32(&w_full[ws]), tap * 64, g * 64);
-          if (!single) tma_load_2d(dst + 64 * 128, &tmBl, smem_u32(&w_full[ws]), tap * 64, g * 64);
+          tma_load_2d(dst, &tmBh, smem_u32(&w_full[ws]), (tap * ncin + gi) * 64, g * 64);
+          if (!single) tma_load_2d(dst + 64 * 128, &tmBl, smem_u32(&w_full[ws]), (tap * ncin + gi) * 64, g * 64);
           if (++ws == RL_NSTAGE) {
             ws = 0;
             if (wrapped) wpar ^= 1;
             wrapped = true;
           }
+        }
         }
       }
     }
@@ -395,10 +405,11 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         const int t = w % ntiles;
         const int yb = t % nyb;
         const int y0 = 2 * yb;
-        const bool fresh = (w == t0) || (yb == 0);
-        const bool next_fresh = (w + 1 < t1) && (((t + 1) % nyb) == 0);
+        const bool fresh = (w == t0) || (yb == 0) || (ncin > 1);
         const int p0 = (y0 >> 1) & 1, p1 = p0 ^ 1;
         if (it >= 2) mbar_wait(smem_u32(&acc_empty[it & 1]), (uint32_t)(((it >> 1) - 1) & 1));
+        for (int gi = 0; gi < ncin; ++gi) {
+        const bool next_fresh = (ncin > 1) ? (gi + 1 < ncin || w + 1 < t1) : ((w + 1 < t1) && (((t + 1) % nyb) == 0));
         if (fresh) {
           mbar_wait(smem_u32(&pair_full[p0]), (uint32_t)((p0 ? nfull1 : nfull0) & 1));
           if (p0) ++nfull1; else ++nfull0;
@@ -431,7 +442,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             const uint32_t ah = rowh[r + ky] + (uint32_t)(kx * 8), al = rowl[r + ky] + (uint32_t)(kx * 8);
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
-              const uint32_t acc = (tap > 0 || k16 > 0) ? 1u : 0u;
+              const uint32_t acc = (gi > 0 || tap > 0 || k16 > 0) ? 1u : 0u;
               const uint32_t tm = tacc + (uint32_t)r * row_stride;
               if (cat) {
                 umma_lo_elect(tm, ah + 2 * k16, bh + 2 * k16, idesc128, acc);   // [hi*hi | hi*lo]
@@ -453,6 +464,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           if (tap == 5) umma_commit_elect(smem_u32(&pair_empty[p0]));   // rows 0, 1 are dead: the next tile's new rows go here
         }
         if (next_fresh) umma_commit_elect(smem_u32(&pair_empty[p1]));   // the next tile reloads both pairs
+        }
         umma_commit_elect(smem_u32(&acc_full[it & 1]));
       }
     }
@@ -741,7 +753,7 @@ static inline long long rup8(long long x) { return (x + 7) & ~7LL; }
 // conv3x3 64 -> Cout (64, 128, 192 or 256) through the TMA kernel.  Returns 0 ok, 1 error, -1 not eligible (caller
 // falls through).  Cout > 64 needs the persistent rolling-halo kernel (mode 3).
 int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, float* Y, int nimg, int H, int W,
-                            int Cout, int single, int a_valid, void* ws, long long ws_bytes, float* stats,
+                            int Cin, int Cout, int single, int a_valid, void* ws, long long ws_bytes, float* stats,
                             cudaStream_t st) {
   static const int mode = []() {          // TATT_TMA: 0 = off, 1 / 2 = one tile per CTA (base_offset 0 / from address),
     const char* e = getenv("TATT_TMA");   //           3 = persistent rolling-halo kernel (default)
@@ -749,24 +761,30 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
   }();
   if (mode == 0 || ws == nullptr || W % TW != 0 || H % 2 != 0) return -1;
   if (Cout % 64 != 0 || Cout < 64 || Cout > 256 || ((Cout != 64 || stats) && mode != 3) || (stats && Cout != 64)) return -1;
-  const int ngroups = Cout / 64;
+  static const int multi_in = []() {      // TATT_ROLL_CIN=0: C_in > 64 goes back to the im2col GEMM engine (A/B timing)
+    const char* e = getenv("TATT_ROLL_CIN");
+    return e ? atoi(e) : 1;
+  }();
+  if (Cin % 64 != 0 || Cin < 64 || Cin > 256 || (Cin != 64 && (mode != 3 || stats || !multi_in || Cout != 64))) return -1;
+  const int ngroups = Cout / 64, K = 9 * Cin;
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;
   const long long P = (long long)nimg * H * W;
-  const long long nA = rup8(P * 64), nB = rup8((long long)Cout * 576);
+  const long long nA = rup8(P * Cin), nB = rup8((long long)Cout * K);
   if ((long long)sizeof(__nv_bfloat16) * 2 * (nA + nB) > ws_bytes || (((uintptr_t)ws) & 15)) return -1;
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16 *Ahi = base, *Alo = base + nA, *Bhi = base + 2 * nA, *Blo = base + 2 * nA + nB;
-  int rc = a_valid ? 0 : tatt_tc2_split(X, 64, P, 64, 0, Ahi, Alo, nullptr, st);   // activations -> [P][64] planes
+  int rc = a_valid ? 0 : tatt_tc2_split(X, Cin, P, Cin, 0, Ahi, Alo, nullptr, st);   // activations -> [P][Cin] planes
   if (rc) return rc;
-  rc = tatt_tc2_split(Wt, Cout, 576, Cout, 1, Bhi, Blo, nullptr, st);        // Wt[576][Cout] -> planes [Cout co][576 k]
+  rc = tatt_tc2_split(Wt, Cout, K, Cout, 1, Bhi, Blo, nullptr, st);          // Wt[9 Cin][Cout] -> planes [Cout co][9 Cin k]
   if (rc) return rc;
 
   constexpr int R = 2;
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
   {
-    cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
-    cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+    const cuuint64_t pxb = (cuuint64_t)Cin * 2;                 // bytes per pixel of a plane
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    cuuint64_t gstr[3] = {pxb, (cuuint64_t)W * pxb, (cuuint64_t)H * W * pxb};
     cuuint32_t box[4] = {64, HALO_W, (cuuint32_t)(mode == 3 ? 2 : R + 2), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     for (int pl = 0; pl < 2; ++pl) {
@@ -777,8 +795,8 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
     }
   }
   {
-    cuuint64_t gdim[2] = {576, (cuuint64_t)Cout};
-    cuuint64_t gstr[1] = {576 * 2};
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {64, 64};
     cuuint32_t estr[2] = {1, 1};
     for (int pl = 0; pl < 2; ++pl) {
@@ -808,19 +826,10 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
       const char* e = getenv("TATT_ROLL_CAT");
       return e ? atoi(e) : 1;
     }();
-    if (single) {
-      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<true, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups,
-                                                             stats);
-    } else if (cat_on) {
-      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<false, true><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups,
-                                                             stats);
-    } else {
-      TATT_CUDA(cudaFuncSetAttribute(conv3x3_roll_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv3x3_roll_kernel<false, false><<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups,
-                                                             stats);
-    }
+    auto* kern = single ? conv3x3_roll_kernel<true, false>
+                        : (cat_on ? conv3x3_roll_kernel<false, true> : conv3x3_roll_kernel<false, false>);
+    TATT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups, stats, Cin / 64);
     TATT_LAUNCH_CHECK("conv3x3_roll_kernel");
     return 0;
   }

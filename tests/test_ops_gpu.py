@@ -66,7 +66,8 @@ def test_gemm_batched_strided():
                                              (1, 1, 2, 256, 256, 3), (2, 8, 8, 3, 64, 9), (2, 8, 8, 64, 3, 9),
                                              (2, 4, 128, 64, 64, 3), (1, 6, 256, 64, 64, 3), (5, 8, 128, 64, 64, 3),
                                              (40, 16, 128, 64, 64, 3), (3, 2, 128, 64, 64, 3),
-                                             (2, 4, 128, 64, 256, 3), (3, 8, 128, 64, 128, 3)])   # last seven: TMA halo kernels (the last two with 4 / 2 output-channel groups); (persistent rolling-halo variant: strips, fresh / rolling tiles, > 148 tiles)
+                                             (2, 4, 128, 64, 256, 3), (3, 8, 128, 64, 128, 3),
+                                             (2, 4, 128, 256, 64, 3), (3, 6, 128, 128, 128, 3)])   # last nine: TMA halo kernels (persistent rolling-halo variant: strips, fresh / rolling tiles, > 148 tiles; then 4 / 2 output-channel groups, whose data gradients -- and the last two cases' forward -- are one accumulating pass per 64-channel input group)
 def test_conv2d_fwd_bwd(N, H, W, Cin, Cout, k):
     from tatt_b200 import ops
     pad = k // 2
