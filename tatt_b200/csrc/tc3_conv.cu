@@ -287,12 +287,13 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
 constexpr int RL_NSTAGE = 4;                                  // weight-tap ring (4 x 16 KB) + 16 KB of epilogue staging
 constexpr int RL_STG_BYTES = 4 * 32 * 128;                    // per epilogue warp: [32 px][32 ch] fp32
 
-template <bool single, bool cat>
+template <bool single, bool cat, bool multi_in>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                     float* __restrict__ Y, const float* __restrict__ bias, int H, int W, int ntiles, int dbg, int ldy,
-                    int ngroups, float* __restrict__ stats, int ncin) {
+                    int ngroups, float* __restrict__ stats, int ncin_rt) {
+  const int ncin = multi_in ? ncin_rt : 1;      // compile-time 1 for the 64-input-channel layers (the tuned path)
   // C_in = 64 * ncin (ncin > 1 only with one output group): every output tile accumulates ncin x 9 taps in its TMEM
   // accumulator, input group gi = channels [64 gi, 64 gi + 64) of the [P][C_in] planes = k columns tap * C_in + 64 gi of
   // the weight planes.  The halo rows of a group cannot roll into the next tile (the four row slots are reloaded per
@@ -826,8 +827,11 @@ int tatt_tc3_conv3x3_launch(const float* X, const float* Wt, const float* bias, 
       const char* e = getenv("TATT_ROLL_CAT");
       return e ? atoi(e) : 1;
     }();
-    auto* kern = single ? conv3x3_roll_kernel<true, false>
-                        : (cat_on ? conv3x3_roll_kernel<false, true> : conv3x3_roll_kernel<false, false>);
+    auto* kern = (Cin > 64)
+                     ? (single ? conv3x3_roll_kernel<true, false, true>
+                               : (cat_on ? conv3x3_roll_kernel<false, true, true> : conv3x3_roll_kernel<false, false, true>))
+                     : (single ? conv3x3_roll_kernel<true, false, false>
+                               : (cat_on ? conv3x3_roll_kernel<false, true, false> : conv3x3_roll_kernel<false, false, false>));
     TATT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, 192, smem, st>>>(tmAh, tmAl, tmBh, tmBl, Y, bias, H, W, ntiles, dbg, Cout, ngroups, stats, Cin / 64);
     TATT_LAUNCH_CHECK("conv3x3_roll_kernel");

@@ -19,6 +19,7 @@
 //                      operands MN-major: a shared-memory row is one pixel's 64 channels), column sums of A or B (the
 //                      bias gradient) accumulated in the loader registers, per-CTA partial tiles + a reduction kernel
 //                      (deterministic, no same-address atomics).
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -107,12 +108,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // 4 consecutive fp32 -> 4 bf16 hi (8 B) + 4 bf16 lo (8 B); element 0 at the lowest address
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
 __device__ __forceinline__ void split4(const float4 a, uint2& hi, uint2& lo) {
-  const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-  const __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2bfloat162_rn(a.z - f1.x, a.w - f1.y);
-  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  // hi = round-to-nearest bf16, lo = bf16(x - hi); the packed hi pair is unpacked with one shift and one mask
+  const uint32_t h0 = pack_bf16x2_rn(a.x, a.y), h1 = pack_bf16x2_rn(a.z, a.w);
+  const float l0x = a.x - __uint_as_float(h0 << 16), l0y = a.y - __uint_as_float(h0 & 0xffff0000u);
+  const float l1x = a.z - __uint_as_float(h1 << 16), l1y = a.w - __uint_as_float(h1 & 0xffff0000u);
+  hi = make_uint2(h0, h1);
+  lo = make_uint2(pack_bf16x2_rn(l0x, l0y), pack_bf16x2_rn(l1x, l1y));
 }
 __device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
   uint2 h0, l0, h1, l1;
@@ -692,25 +699,298 @@ __global__ void __launch_bounds__(NT, 2) rows_wgrad_kernel(const WgP p) {
   }
 }
 
-// D[r][c] = sum over the per-CTA partial tiles (coalesced reads, 4 part groups per element, fixed summation order),
+// Warp-specialised variant (the default for large M): ONE CTA per SM = 8 converter warps + 1 MMA warp + 1 TMA warp.
+//   * The two kernels above prefetch through registers.  All LDGs of a warp share ONE scoreboard (checked in the SASS:
+//     every LDG of the 4-deep register ring of an earlier version of this kernel carried write-barrier 5), so waiting
+//     for the oldest slab waits for the newest one too: the prefetch depth is 1 whatever the source says, and both
+//     kernels sit at 3.0 - 3.7 TB/s = what <= 64 KB per SM in flight buys at the loaded HBM latency.
+//   * Here the fp32 slabs arrive by TMA (completion on mbarriers, any depth) into a ring of SEVEN 32 KB buffers.  A
+//     buffer goes  empty -> [TMA] fp32 slab [128][64] -> [converters, IN PLACE: all 256 threads read their 8 float4, one
+//     named barrier, then write the bf16 hi | lo planes (2 x 16 KB) over them] -> [MMA warp] -> tcgen05.commit -> empty.
+//     Typically 3 - 4 buffers are filling (96 - 128 KB per SM in flight), one is being converted, two or three (the
+//     block's A slab + the B slabs in the tensor pipe) are being read.  Rows past M are zero-filled by the TMA unit.
+//   * ONE MMA per k-step instead of three: the second 64-channel block of both descriptors (leading-dimension byte
+//     offset = PLANE) is the LO plane of the same slab, so a single M = 128, N = 128 MMA [A_hi ; A_lo] x [B_hi | B_lo]
+//     leaves hi*hi, hi*lo, lo*hi and lo*lo in the four 64 x 64 quadrants of the accumulator (8 KB of operand fetch per
+//     k-step instead of 3 x 6 KB; these MN-major MMAs are bound by shared-memory operand fetch, ~100 cycles each).  The
+//     epilogue adds the quadrants.  (The older kernels issue three M = 128, N = 64 MMAs and throw the upper halves away.)
+//   Stream order per CTA: for each of its 128-row blocks k: A_k, B0_k .. B(NB-1)_k; slab n lives in buffer n % 7.
+constexpr int WS_CONV_WARPS = 8;
+constexpr int WS_NT = 32 * (WS_CONV_WARPS + 2);
+constexpr int WS_NBUF = 7;
+constexpr int WS_BUF = 2 * PLANE;               // 32 KB: one fp32 slab = its two bf16 planes
+constexpr int WS_SMEM = WS_NBUF * WS_BUF + 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+struct WsMaps {
+  CUtensorMap a0, a1;          // A columns a_off0..+32 / a_off1..+32: [M rows][32] fp32, box [128][32]
+  CUtensorMap b[3];            // B slabs: [M rows][64] fp32, box [128][64]
+};
+
+template <int NB>
+__global__ void __launch_bounds__(WS_NT, 1) rows_wgrad_ws_kernel(const __grid_constant__ WsMaps tm, const WgP p) {
+  constexpr uint32_t TCOLS = (NB == 1) ? 128u : ((NB == 2) ? 256u : 512u);   // 128 accumulator columns per B slab
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long full_raw[WS_NBUF], full_pl[WS_NBUF], empty[WS_NBUF], done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[WG_LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool single = (p.flags & F_BF16) != 0;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (tid == 0) {
+    for (int i = 0; i < WS_NBUF; ++i) {
+      mbar_init(smem_u32(&full_raw[i]), 1);
+      mbar_init(smem_u32(&full_pl[i]), 32 * WS_CONV_WARPS);
+      mbar_init(smem_u32(&empty[i]), 1);
+    }
+    mbar_init(smem_u32(&done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == WS_CONV_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(TCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < WG_LD; i += WS_NT) red[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int g = gridDim.x;
+  const int nk = (p.nblk - (int)blockIdx.x + g - 1) / g;     // blocks of this CTA: blockIdx.x + k g
+  float cs[NB][4];
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cs[j][q] = 0.f;
+  const int c4 = tid & 15;
+
+  if (warp < WS_CONV_WARPS) {
+    // ------------------------------------------------------------ converters: fp32 slab -> bf16 hi | lo planes, in place
+    const int r0 = tid >> 4;
+    const uint32_t st_off = (uint32_t)slab_st_off(tid);
+    const uint32_t src_a = (uint32_t)((c4 >> 3) * PLANE + r0 * 128 + (c4 & 7) * 16);   // two [128][32] boxes
+    const uint32_t src_b = (uint32_t)(r0 * 256 + c4 * 16);                              // one [128][64] box
+    int b = 0;
+    uint32_t par = 0;
+    for (int k = 0; k < nk; ++k) {
+#pragma unroll
+      for (int sj = 0; sj <= NB; ++sj) {
+        const uint32_t buf = sbase + (uint32_t)(b * WS_BUF);
+        mbar_wait(smem_u32(&full_raw[b]), par);
+        Slab cur;
+        if (sj == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cur.v[i] = lds128(buf + src_a + i * 2048);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cur.v[i] = lds128(buf + src_b + i * 4096);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // every converter holds its part: the planes may overwrite the slab
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint2 h, l;
+          split4(cur.v[i], h, l);
+          sts64(buf + st_off + i * 2048, h);
+          if (!single) sts64(buf + PLANE + st_off + i * 2048, l);
+        }
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_pl[b]));
+        if (sj == 0) {
+          if (p.colsum_src == 1) slab_colsum(cur, cs[0]);
+        } else {
+          if (p.colsum_src == 2) slab_colsum(cur, cs[(sj > 0) ? (sj - 1) : 0]);
+        }
+        if (++b == WS_NBUF) {
+          b = 0;
+          par ^= 1;
+        }
+      }
+    }
+  } else if (warp == WS_CONV_WARPS) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+    // M = 128, N = 128 (bf16 mode: 64, the lo planes do not exist), A and B MN-major (bits 15, 16)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)((single ? 64 : 128) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int b = 0;
+    uint32_t par = 0;
+    for (int k = 0; k < nk; ++k) {
+      const int ba = b;
+      mbar_wait(smem_u32(&full_pl[ba]), par);
+      const uint32_t ah = sbase + (uint32_t)(ba * WS_BUF);
+      if (++b == WS_NBUF) {
+        b = 0;
+        par ^= 1;
+      }
+#pragma unroll
+      for (int sj = 0; sj < NB; ++sj) {
+        mbar_wait(smem_u32(&full_pl[b]), par);
+        tc_fence_after();
+        const uint32_t bh = sbase + (uint32_t)(b * WS_BUF);
+        const uint32_t tmc = tmem_base + (uint32_t)(sj * 128);
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16) {
+          const uint32_t ko = k16 * 2048;   // 16 pixel rows = two 8-row groups of 1024 B
+          umma_bf16_elect(tmc, make_desc(ah + ko, PLANE, 1024), make_desc(bh + ko, PLANE, 1024), idesc,
+                          (k == 0 && k16 == 0) ? 0u : 1u);
+        }
+        umma_commit_elect(smem_u32(&empty[b]));
+        if (++b == WS_NBUF) {
+          b = 0;
+          par ^= 1;
+        }
+      }
+      umma_commit_elect(smem_u32(&empty[ba]));
+    }
+    umma_commit_elect(smem_u32(&done));
+  } else {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int b = 0;
+      uint32_t par = 0;
+      bool wrapped = false;
+      for (int k = 0; k < nk; ++k) {
+        const int row0 = ((int)blockIdx.x + k * g) * RB;
+#pragma unroll
+        for (int sj = 0; sj <= NB; ++sj) {
+          if (wrapped) mbar_wait(smem_u32(&empty[b]), par ^ 1u);
+          const uint32_t buf = sbase + (uint32_t)(b * WS_BUF), bar = smem_u32(&full_raw[b]);
+          mbar_expect_tx(bar, (uint32_t)WS_BUF);
+          if (sj == 0) {
+            tma_load_2d(buf, &tm.a0, bar, 0, row0);
+            tma_load_2d(buf + PLANE, &tm.a1, bar, 0, row0);
+          } else {
+            tma_load_2d(buf, &tm.b[sj - 1], bar, 0, row0);
+          }
+          if (++b == WS_NBUF) {
+            b = 0;
+            par ^= 1;
+            wrapped = true;
+          }
+        }
+      }
+    }
+  }
+  mbar_wait(smem_u32(&done), 0u);
+  tc_fence_after();
+  float* part = p.partial + (long long)blockIdx.x * WG_PART;
+  const int lg = warp & 3, half = warp >> 2;
+  if (warp < WS_CONV_WARPS) {
+    // rows 64..127 (the A_lo products; TMEM lane groups 2, 3) go through shared memory (the ring is dead) to the warps
+    // that own rows 0..63.  bf16 mode: the lo planes were never written (stale slab bytes), rows 64..127 are ignored.
+    constexpr int SLD = 196;                      // floats per staged row: 16-byte aligned, rows 4 banks apart
+    float* stg = reinterpret_cast<float*>(smem);
+    const int row = (lg & 1) * 32 + lane;
+    uint32_t v[NB][2][16];
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+#pragma unroll
+      for (int c16 = 0; c16 < 2; ++c16) {
+        const uint32_t tcol = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(j * 128 + half * 32 + c16 * 16);
+        tmem_ld16(tcol, v[j][c16]);
+        if (!single) {                              // + the B_lo column block
+          uint32_t v2[16];
+          tmem_ld16(tcol + 64, v2);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[j][c16][q] = __float_as_uint(__uint_as_float(v[j][c16][q]) + __uint_as_float(v2[q]));
+        }
+      }
+    if (lg >= 2) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
+          float4* dst = reinterpret_cast<float4*>(stg + row * SLD + j * 64 + half * 32 + c16 * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(__uint_as_float(v[j][c16][4 * q]), __uint_as_float(v[j][c16][4 * q + 1]),
+                                 __uint_as_float(v[j][c16][4 * q + 2]), __uint_as_float(v[j][c16][4 * q + 3]));
+        }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight converter warps
+    if (lg < 2) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
+          const int col0 = j * 64 + half * 32 + c16 * 16;
+          const float4* lo4 = reinterpret_cast<const float4*>(stg + row * SLD + col0);
+          float4* dst = reinterpret_cast<float4*>(part + row * WG_LD + col0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 l = lo4[q];
+            if (single) l = make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[q] = make_float4(__uint_as_float(v[j][c16][4 * q]) + l.x, __uint_as_float(v[j][c16][4 * q + 1]) + l.y,
+                                 __uint_as_float(v[j][c16][4 * q + 2]) + l.z, __uint_as_float(v[j][c16][4 * q + 3]) + l.w);
+          }
+        }
+    }
+  }
+  if (p.colsum_src) {
+    if (warp < WS_CONV_WARPS) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (j == 0 || p.colsum_src == 2) atomicAdd(&red[j * 64 + c4 * 4 + q], cs[j][q]);
+    }
+    __syncthreads();
+    for (int i = tid; i < WG_LD; i += WS_NT) part[64 * WG_LD + i] = red[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WS_CONV_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
+  }
+}
+
+// D[r][c] = sum over the per-CTA partial tiles (coalesced reads, 16 part groups per element, fixed summation order),
 // then scattered to out[b][i][j] with D[b rb + (T ? j : i)][b cb + (T ? i : j)];  rows >= 64 of the index space are the
 // column sums -> dbias
-__global__ void __launch_bounds__(256) rows_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts,
-                                                               float* __restrict__ out, int nb, int ni, int nj, int T,
-                                                               int rb, int cb, float* __restrict__ dbias, int nbias,
-                                                               int ncols) {
-  __shared__ float sm[4][64];
+__global__ void __launch_bounds__(1024) rows_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts,
+                                                                float* __restrict__ out, int nb, int ni, int nj, int T,
+                                                                int rb, int cb, float* __restrict__ dbias, int nbias,
+                                                                int ncols) {
+  // 16 part groups per element (a 4-group version spent 11 us per call on ~40 dependent-latency loads per thread)
+  __shared__ float sm[16][64];
   const int e = threadIdx.x & 63, g = threadIdx.x >> 6;
   const int row = blockIdx.x / 3, c = (blockIdx.x % 3) * 64 + e;       // row 64 = the column sums
   float a = 0.f;
   if (c < ncols) {
     const float* src = partial + (long long)row * WG_LD + c;
-    for (int q = g; q < nparts; q += 4) a += src[(long long)q * WG_PART];
+#pragma unroll 4
+    for (int q = g; q < nparts; q += 16) a += src[(long long)q * WG_PART];
   }
   sm[g][e] = a;
   __syncthreads();
   if (g != 0 || c >= ncols) return;
-  a = (sm[0][e] + sm[1][e]) + (sm[2][e] + sm[3][e]);
+  a = 0.f;
+#pragma unroll
+  for (int q = 0; q < 16; q += 4) a += (sm[q][e] + sm[q + 1][e]) + (sm[q + 2][e] + sm[q + 3][e]);
   if (row == 64) {
     if (c < nbias) dbias[c] = a;
     return;
@@ -737,6 +1017,47 @@ static int launch_rows_gemm(const RowsP& p, cudaStream_t st) {
   TATT_CUDA(cudaFuncSetAttribute(rows_gemm_kernel<NB, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   rows_gemm_kernel<NB, KB><<<grid, NT, smem, st>>>(p);
   TATT_LAUNCH_CHECK("rows_gemm_kernel");
+  return 0;
+}
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+// fp32 [M rows][cols] view with row stride ld (elements), box [128 rows][cols]; rows past M read as zeros
+static bool encode_slab_map(CUtensorMap* m, const float* base, long long ld, long long M, int cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)M};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)cols, (cuuint32_t)RB};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// -1: the TMA path cannot serve this call (no driver entry point / descriptor rejected): the caller falls back
+template <int NB>
+static int launch_rows_wgrad_ws(const WgP& p, int grid, cudaStream_t st) {
+  WsMaps tm;
+  if (!encode_slab_map(&tm.a0, p.A + p.a_off0, p.lda, p.M, 32) || !encode_slab_map(&tm.a1, p.A + p.a_off1, p.lda, p.M, 32))
+    return -1;
+  const float* bs[3] = {p.B0, p.B1, p.B2};
+  const long long ls[3] = {p.ldb0, p.ldb1, p.ldb2};
+  for (int j = 0; j < 3; ++j)
+    if (!encode_slab_map(&tm.b[j], bs[j < NB ? j : 0], ls[j < NB ? j : 0], p.M, 64)) return -1;
+  TATT_CUDA(cudaFuncSetAttribute(rows_wgrad_ws_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+  rows_wgrad_ws_kernel<NB><<<grid, WS_NT, WS_SMEM, st>>>(tm, p);
+  TATT_LAUNCH_CHECK("rows_wgrad_ws_kernel");
   return 0;
 }
 template <int NB>
@@ -811,19 +1132,38 @@ int tatt_rows_wgrad(const float* A, long long lda, int a_off0, int a_off1, const
   p.M = M;
   p.nblk = (int)((M + RB - 1) / RB);
   p.colsum_src = colsum_src; p.flags = flags;
-  int grid = 2 * num_sms();
-  if (grid > WG_MAX_GRID) grid = WG_MAX_GRID;
-  if (grid > p.nblk) grid = p.nblk;
-  TATT_REQUIRE((long long)grid * WG_PART * (long long)sizeof(float) <= ws_bytes,
-               "tatt_rows_wgrad: workspace too small (%lld bytes, need %lld)", ws_bytes,
-               (long long)grid * WG_PART * (long long)sizeof(float));
-  p.partial = reinterpret_cast<float*>(ws);
+  // TATT_WG_WS=0: the register-prefetch kernels at two CTAs per SM (A/B timing); the warp-specialised TMA kernel runs one
+  // CTA per SM and needs a few blocks per CTA to fill its ring
+  static const int ws_on = []() {
+    const char* e = getenv("TATT_WG_WS");
+    return e ? atoi(e) : 1;
+  }();
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = (NB == 1) ? launch_rows_wgrad<1>(p, grid, st) : ((NB == 2) ? launch_rows_wgrad<2>(p, grid, st)
-                                                                     : launch_rows_wgrad<3>(p, grid, st));
+  p.partial = reinterpret_cast<float*>(ws);
+  int rc = -1, nparts = 0;
+  if (ws_on && p.nblk >= 2 * num_sms()) {
+    const int grid = num_sms() < WG_MAX_GRID ? num_sms() : WG_MAX_GRID;
+    TATT_REQUIRE((long long)grid * WG_PART * (long long)sizeof(float) <= ws_bytes,
+                 "tatt_rows_wgrad: workspace too small (%lld bytes, need %lld)", ws_bytes,
+                 (long long)grid * WG_PART * (long long)sizeof(float));
+    rc = (NB == 1) ? launch_rows_wgrad_ws<1>(p, grid, st)
+                   : ((NB == 2) ? launch_rows_wgrad_ws<2>(p, grid, st) : launch_rows_wgrad_ws<3>(p, grid, st));
+    nparts = grid;
+  }
+  if (rc < 0) {
+    int grid = 2 * num_sms();
+    if (grid > WG_MAX_GRID) grid = WG_MAX_GRID;
+    if (grid > p.nblk) grid = p.nblk;
+    TATT_REQUIRE((long long)grid * WG_PART * (long long)sizeof(float) <= ws_bytes,
+                 "tatt_rows_wgrad: workspace too small (%lld bytes, need %lld)", ws_bytes,
+                 (long long)grid * WG_PART * (long long)sizeof(float));
+    rc = (NB == 1) ? launch_rows_wgrad<1>(p, grid, st)
+                   : ((NB == 2) ? launch_rows_wgrad<2>(p, grid, st) : launch_rows_wgrad<3>(p, grid, st));
+    nparts = grid;
+  }
   if (rc) return rc;
-  rows_wgrad_reduce_kernel<<<(64 + (colsum_src ? 1 : 0)) * 3, 256, 0, st>>>(
-      p.partial, grid, out, nb, ni, nj, transpose, rb, cb, dbias, colsum_src ? nbias : 0, 64 * NB);
+  rows_wgrad_reduce_kernel<<<(64 + (colsum_src ? 1 : 0)) * 3, 1024, 0, st>>>(
+      p.partial, nparts, out, nb, ni, nj, transpose, rb, cb, dbias, colsum_src ? nbias : 0, 64 * NB);
   TATT_LAUNCH_CHECK("rows_wgrad_reduce_kernel");
   return 0;
 }

@@ -69,7 +69,7 @@ def test_rows_gemm_two_sources():
     close(y, ref, 2e-4, "rows_gemm cat")
 
 
-@pytest.mark.parametrize("M", [128, 777, 50000])
+@pytest.mark.parametrize("M", [128, 777, 50000, 100003])   # >= 4 x 148 row blocks: the warp-specialised kernel
 @pytest.mark.parametrize("N,K", [(64, 64), (64, 128), (192, 64), (128, 64)])
 def test_rows_wgrad(M, N, K):
     from tatt_b200 import ops
@@ -83,9 +83,9 @@ def test_rows_wgrad(M, N, K):
     close(dW2, dy.double().t() @ x.double(), 5e-4, "rows_wgrad dW (no bias)")
 
 
-def test_rows_wgrad_parts_and_gates():
+@pytest.mark.parametrize("M", [5000, 90001])
+def test_rows_wgrad_parts_and_gates(M):
     from tatt_b200 import ops
-    M = 5000
     dy, p0, p1 = g(M, 64, seed=3), g(M, 64), g(M, 64, seed=7)
     dW, db = ops.linear_bwd_weight_rows_parts(dy.to(dev()), [p0.to(dev()), p1.to(dev())], True)
     close(dW, dy.double().t() @ torch.cat([p0, p1], 1).double(), 5e-4, "wgrad cat")
@@ -102,9 +102,9 @@ def test_rows_wgrad_parts_and_gates():
     close(dbhh, dgh.double().sum(0), 5e-4, "db_hh")
 
 
-def test_rows_bf16_mode():
+@pytest.mark.parametrize("M", [4096, 131072])
+def test_rows_bf16_mode(M):
     from tatt_b200 import ops
-    M = 4096
     x, w, b, dy = g(M, 64), g(192, 64, seed=1, scale=0.2), g(192, seed=2), g(M, 192, seed=3)
     ops.set_precision("bf16")
     try:

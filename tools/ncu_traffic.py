@@ -15,7 +15,11 @@ import sys
 ENTRY = {
     "tc2_gemm_kernel<0, 4>": "tatt_gemm M128 N1024 K3072 x2",
     "rows_wgrad1_kernel<3>": "tatt_rows_wgrad NB3",
+    "rows_wgrad_ws_kernel<3>": "tatt_rows_wgrad NB3",
+    "rows_wgrad_ws_kernel<2>": "tatt_rows_wgrad NB2",
+    "rows_wgrad_ws_kernel<1>": "tatt_rows_wgrad NB1",
     "conv3x3_roll_kernel<0, 1>": "tatt_conv2d_igemm 3x3 64->64",
+    "conv3x3_roll_kernel<0, 1, 0>": "tatt_conv2d_igemm 3x3 64->64",
     "mha_bwd_kernel": "tatt_mha64_bwd ",
     "mha_bwd_mma_kernel": "tatt_mha64_bwd ",
     "rows_wgrad_kernel<1>": "tatt_rows_wgrad NB1",
@@ -29,7 +33,8 @@ ENTRY = {
     "rows_gemm_kernel<1, 1>": "tatt_rows_gemm K64 N64",
     "rows_gemm_kernel<3, 1>": "tatt_rows_gemm K64 N192",
 }
-ALIAS = {"conv3x3_roll_kernel<0, 1>": ["tatt_conv3x3_stats 3x3 64->64"]}      # same kernel behind a second entry point
+ALIAS = {"conv3x3_roll_kernel<0, 1>": ["tatt_conv3x3_stats 3x3 64->64"],
+         "conv3x3_roll_kernel<0, 1, 0>": ["tatt_conv3x3_stats 3x3 64->64"]}      # same kernel behind a second entry point
 COLS = {"dur": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram__bytes_write.sum",
         "tensor": "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
         "tensor2": "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
