@@ -19,6 +19,9 @@
 //                      operands MN-major: a shared-memory row is one pixel's 64 channels), column sums of A or B (the
 //                      bias gradient) accumulated in the loader registers, per-CTA partial tiles + a reduction kernel
 //                      (deterministic, no same-address atomics).
+//   rows_wgrad_ws_kernel  the same product for large P (the default there): warp-specialised, fp32 slabs by TMA into a
+//                      7-buffer shared-memory ring, split IN PLACE into the hi | lo planes, one M = 128 x N = 128 MMA per
+//                      k-step ([A_hi ; A_lo] x [B_hi | B_lo]: all four hi/lo products in the accumulator's quadrants).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
